@@ -1,0 +1,687 @@
+// dto_engine.cu -- low-level C ABI (integer ids): context, problem upload, batched task execution.
+// Replaces the per-task body of run::run_single_node's worker loop (src/run/single_node.rs:114-123, i.e.
+// dto::optimize -> process_threshold_pairs) with batched kernel launches.  No CPU fallback exists: every
+// entry point fails with DTO_B200_ERR_CUDA when the device is unusable.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dto_host_math.hpp"
+#include "dto_internal.hpp"
+#include "dto_kernels.cuh"
+
+namespace dto {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(DTO_B200_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, \
+                        __LINE__, #expr);                                                                   \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes ? bytes : 16;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes ? bytes : 16;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+}  // namespace dto
+
+using namespace dto;
+
+struct dto_b200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool has_problem = false;
+    Problem P{};
+    // problem tables
+    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2;
+    // batch state
+    DevBuf d_pb, d_records, d_status, d_counters, d_taskids, d_wide, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
+        d_err, d_pair, d_minp;
+    PinnedBuf h_records, h_status, h_stage;
+    // options
+    int opt_batch = 0;  // 0 = auto
+    int opt_warps = 8;
+    int opt_levels = 12;
+    dto_b200_stats stats{};
+};
+
+namespace {
+
+int bind(dto_b200_ctx *ctx) {
+    if (!ctx) return fail(DTO_B200_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return DTO_B200_OK;
+}
+
+int auto_batch(const dto_b200_ctx *ctx) {
+    if (ctx->opt_batch > 0) return ctx->opt_batch;
+    // enough permutations for several full waves of warps, bounded by ~1 GiB of partner-slot rows
+    const size_t row_bytes = (size_t)ctx->P.pb_stride * 2;
+    size_t b = (size_t)ctx->sm_count * 2 * ctx->opt_warps * 8;
+    const size_t cap = ((size_t)1 << 30) / (row_bytes ? row_bytes : 1);
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// Runs the scan over n tasks whose partner-slot rows are already in ctx->d_pb; results land in
+// ctx->d_records[0..n).  Escalates overflowed tasks to the wide kernel and degenerate ones to the dense path.
+int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags) {
+    const Problem &P = ctx->P;
+    CUDA_TRY(ctx->d_records.ensure((size_t)n * sizeof(dto_b200_record)));
+    CUDA_TRY(ctx->d_status.ensure((size_t)n * 4));
+    CUDA_TRY(ctx->h_status.ensure((size_t)n * 4));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_status.p, 0xFF, (size_t)n * 4, ctx->stream));
+    int warps = ctx->opt_warps;
+    while (warps > 1 && scan_smem_bytes(P.CH, false, P.T1, warps) > ctx->smem_optin / ((P.CH > 32) ? 1 : 2)) --warps;
+    if (scan_smem_bytes(P.CH, false, P.T1, warps) > ctx->smem_optin)
+        return fail(DTO_B200_ERR_UNSUPPORTED, "scan kernel does not fit shared memory (T1=%d T2=%d)", P.T1, P.T2);
+    const int ctas_needed = (n + warps - 1) / warps;
+    const int grid = std::min(ctas_needed, ctx->sm_count * 2);
+    CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+    CUDA_TRY(launch_scan(P, false, ctx->d_pb.as<uint16_t>(), nullptr, n, flags, ctx->d_records.as<dto_b200_record>(),
+                         ctx->d_status.as<uint32_t>(), nullptr, ctx->d_counters.as<unsigned long long>(), grid, warps,
+                         ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.last_scan_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.last_scan_kernel_ms += ms;
+
+    const uint32_t *st = ctx->h_status.as<uint32_t>();
+    std::vector<uint32_t> wide, full;
+    for (int t = 0; t < n; ++t) {
+        if (st[t] == 0) continue;
+        if (st[t] == 1) wide.push_back((uint32_t)t);
+        else if (st[t] == 2) full.push_back((uint32_t)t);
+        else return fail(DTO_B200_ERR_CUDA, "scan kernel left task %d unprocessed (status %u)", t, st[t]);
+    }
+    ctx->stats.tasks_fast += (uint64_t)(n - (int)wide.size() - (int)full.size());
+    if (!wide.empty()) {
+        const int wwarps = 4, wgrid_max = 8;
+        const size_t slot_bytes = (size_t)P.T1 * P.T2 * cand_bytes();
+        const int wgrid = std::min(wgrid_max, (int)((wide.size() + wwarps - 1) / wwarps));
+        CUDA_TRY(ctx->d_wide.ensure(slot_bytes * wwarps * wgrid));
+        CUDA_TRY(ctx->d_taskids.ensure(wide.size() * 4));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_taskids.p, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(launch_scan(P, true, ctx->d_pb.as<uint16_t>(), ctx->d_taskids.as<uint32_t>(), (int)wide.size(), flags,
+                             ctx->d_records.as<dto_b200_record>(), ctx->d_status.as<uint32_t>(), ctx->d_wide.p,
+                             ctx->d_counters.as<unsigned long long>(), wgrid, wwarps, ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t t : wide) {
+            if (st[t] == 2) full.push_back(t);
+            else if (st[t] != 0) return fail(DTO_B200_ERR_CUDA, "wide scan failed on task %u (status %u)", t, st[t]);
+            else ctx->stats.tasks_wide += 1;
+        }
+    }
+    if (!full.empty()) {
+        const size_t cells = (size_t)P.T1 * P.T2;
+        CUDA_TRY(ctx->d_H.ensure(cells * 4));
+        CUDA_TRY(ctx->d_pv.ensure(cells * 8));
+        for (uint32_t t : full) {
+            CUDA_TRY(launch_full_grid(P, ctx->d_pb.as<uint16_t>() + (size_t)t * P.pb_stride, ctx->d_H.as<uint32_t>(),
+                                      ctx->d_pv.as<double>(), nullptr, ctx->stream));
+            CUDA_TRY(launch_full_argmin(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), flags,
+                                        ctx->d_records.as<dto_b200_record>() + t, ctx->stream));
+            ctx->stats.kernel_launches += 5;
+            ctx->stats.tasks_full += 1;
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return DTO_B200_OK;
+}
+
+int need_problem(dto_b200_ctx *ctx) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!ctx->has_problem) return fail(DTO_B200_ERR_STATE, "no problem loaded: call dto_b200_set_problem first");
+    return DTO_B200_OK;
+}
+
+int pull_counters(dto_b200_ctx *ctx) {
+    unsigned long long c[4];
+    CUDA_TRY(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    ctx->stats.candidates = c[0];
+    ctx->stats.level2_cells = c[1];
+    return DTO_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *dto_b200_last_error(void) { return g_last_error.c_str(); }
+const char *dto_b200_version(void) { return "dto-b200 0.1.0 (sm_100a)"; }
+
+int dto_b200_device_count(int *count_out) {
+    if (!count_out) return fail(DTO_B200_ERR_INVALID, "null count_out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count_out = 0;
+        return fail(DTO_B200_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count_out = n;
+    return DTO_B200_OK;
+}
+
+int dto_b200_create(dto_b200_ctx **ctx_out, int device) {
+    if (!ctx_out) return fail(DTO_B200_ERR_INVALID, "null ctx_out");
+    *ctx_out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(DTO_B200_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(DTO_B200_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(DTO_B200_ERR_CUDA, "device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major,
+                    prop.minor);
+    dto_b200_ctx *ctx = new dto_b200_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(DTO_B200_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    for (auto &ev : ctx->ev) cudaEventCreate(&ev);
+    if (ctx->d_counters.ensure(64) != cudaSuccess || ctx->d_err.ensure(16) != cudaSuccess) {
+        dto_b200_destroy(ctx);
+        return fail(DTO_B200_ERR_CUDA, "cudaMalloc failed");
+    }
+    cudaMemset(ctx->d_counters.p, 0, 64);
+    *ctx_out = ctx;
+    return DTO_B200_OK;
+}
+
+void dto_b200_destroy(dto_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_c1, &ctx->d_c2, &ctx->d_thr1, &ctx->d_thr2, &ctx->d_lf, &ctx->d_rowA, &ctx->d_colB,
+                      &ctx->d_kcrit, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
+                      &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_taskids, &ctx->d_wide, &ctx->d_H,
+                      &ctx->d_pv, &ctx->d_logp, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_err, &ctx->d_pair,
+                      &ctx->d_minp};
+    for (DevBuf *b : bufs) b->release();
+    ctx->h_records.release();
+    ctx->h_status.release();
+    ctx->h_stage.release();
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return fail(DTO_B200_ERR_INVALID, "null argument");
+    const std::string s(name);
+    if (s == "batch") {
+        if (value < 0 || value > (1 << 22)) return fail(DTO_B200_ERR_INVALID, "batch out of range");
+        ctx->opt_batch = (int)value;
+    } else if (s == "warps_per_cta") {
+        if (value < 1 || value > kScanThreads / 32) return fail(DTO_B200_ERR_INVALID, "warps_per_cta must be 1..8");
+        ctx->opt_warps = (int)value;
+    } else if (s == "levels") {
+        if (value < 0 || value > kMaxLevels) return fail(DTO_B200_ERR_INVALID, "levels must be 0..%d", kMaxLevels);
+        if (ctx->has_problem) return fail(DTO_B200_ERR_STATE, "set 'levels' before dto_b200_set_problem");
+        ctx->opt_levels = (int)value;
+    } else {
+        return fail(DTO_B200_ERR_INVALID, "unknown option '%s'", name);
+    }
+    return DTO_B200_OK;
+}
+
+int dto_b200_get_stats(dto_b200_ctx *ctx, dto_b200_stats *out) {
+    if (!ctx || !out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    int rc = bind(ctx);
+    if (rc) return rc;
+    rc = pull_counters(ctx);
+    if (rc) return rc;
+    *out = ctx->stats;
+    return DTO_B200_OK;
+}
+
+int dto_b200_reset_stats(dto_b200_ctx *ctx) {
+    if (!ctx) return fail(DTO_B200_ERR_INVALID, "null context");
+    int rc = bind(ctx);
+    if (rc) return rc;
+    ctx->stats = dto_b200_stats{};
+    CUDA_TRY(cudaMemset(ctx->d_counters.p, 0, 64));
+    return DTO_B200_OK;
+}
+
+int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, const uint32_t *thr1, size_t T1,
+                         const uint32_t *ranks2, size_t n2, const uint32_t *thr2, size_t T2,
+                         const int32_t *slot2_of_1, uint64_t population) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    ctx->has_problem = false;
+    if ((n1 && !ranks1) || (n2 && !ranks2) || (T1 && !thr1) || (T2 && !thr2) || (n1 && !slot2_of_1))
+        return fail(DTO_B200_ERR_INVALID, "null input array");
+    if (T1 == 0 || T2 == 0)
+        return fail(DTO_B200_ERR_PANIC,
+                    "called `Option::unwrap()` on a `None` value: a ranked list has no thresholds (empty list or "
+                    "max rank 0; optimize_main.rs:116)");
+    if (n1 > 65534 || n2 > 65534)
+        return fail(DTO_B200_ERR_UNSUPPORTED, "lists longer than 65534 features are not supported (n1=%zu n2=%zu)", n1, n2);
+    if (T1 > 2048 || T2 > 2048) return fail(DTO_B200_ERR_UNSUPPORTED, "more than 2048 thresholds per list");
+    if (population > ((uint64_t)1 << 27))
+        return fail(DTO_B200_ERR_UNSUPPORTED, "population %llu exceeds the ln-factorial table limit (2^27)",
+                    (unsigned long long)population);
+    for (size_t j = 1; j < n1; ++j)
+        if (ranks1[j] < ranks1[j - 1]) return fail(DTO_B200_ERR_INVALID, "ranks1 must be sorted ascending");
+    for (size_t j = 1; j < n2; ++j)
+        if (ranks2[j] < ranks2[j - 1]) return fail(DTO_B200_ERR_INVALID, "ranks2 must be sorted ascending");
+    for (size_t i = 1; i < T1; ++i)
+        if (thr1[i] <= thr1[i - 1]) return fail(DTO_B200_ERR_INVALID, "thresholds1 must be strictly increasing");
+    for (size_t i = 1; i < T2; ++i)
+        if (thr2[i] <= thr2[i - 1]) return fail(DTO_B200_ERR_INVALID, "thresholds2 must be strictly increasing");
+    std::vector<uint8_t> seen(n2, 0);
+    uint32_t n_common = 0;
+    for (size_t a = 0; a < n1; ++a) {
+        const int32_t s = slot2_of_1[a];
+        if (s < 0) continue;
+        if ((size_t)s >= n2) return fail(DTO_B200_ERR_INVALID, "slot2_of_1[%zu]=%d out of range", a, s);
+        if (seen[s]) return fail(DTO_B200_ERR_INVALID, "slot2_of_1 is not injective (list-2 slot %d used twice)", s);
+        seen[s] = 1;
+        ++n_common;
+    }
+
+    Problem P{};
+    P.T1 = (int)T1;
+    P.T2 = (int)T2;
+    P.CH = pick_ch((int)T2);
+    P.CHP = P.CH | 1;
+    P.T2pad = 32 * P.CH;
+    P.levels = ctx->opt_levels;
+    P.n1 = (uint32_t)n1;
+    P.n2 = (uint32_t)n2;
+    P.N = population;
+    P.n_common = n_common;
+    std::vector<uint32_t> c1(T1), c2(T2);
+    for (size_t i = 0; i < T1; ++i) c1[i] = (uint32_t)(std::upper_bound(ranks1, ranks1 + n1, thr1[i]) - ranks1);
+    for (size_t i = 0; i < T2; ++i) c2[i] = (uint32_t)(std::upper_bound(ranks2, ranks2 + n2, thr2[i]) - ranks2);
+    if (c1[T1 - 1] > population || c2[T2 - 1] > population)
+        return fail(DTO_B200_ERR_PANIC,
+                    "Failed to create hypergeometric distribution: a feature set (%u / %u) is larger than the population "
+                    "(%llu)",
+                    c1[T1 - 1], c2[T2 - 1], (unsigned long long)population);
+    P.n1_eff = c1[T1 - 1];
+    P.pb_stride = ((P.n1_eff + 64 + 63) / 64) * 64;
+    std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(n2 ? n2 : 1);
+    for (size_t j = 0; j < n1; ++j) {
+        const size_t b = std::lower_bound(thr1, thr1 + T1, ranks1[j]) - thr1;
+        bin1[j] = b < T1 ? (uint16_t)b : kNoSlot;
+    }
+    for (size_t j = 0; j < n2; ++j) {
+        const size_t b = std::lower_bound(thr2, thr2 + T2, ranks2[j]) - thr2;
+        bin2[j] = b < T2 ? (uint16_t)b : kNoSlot;
+        dslot2[j] = b < T2 ? (uint16_t)((b / P.CH) * P.CHP + (b % P.CH)) : kNoSlot;
+    }
+    std::vector<double> lf;
+    host_fill_ln_factorial(lf, population);
+    std::vector<double> rowA(T1), colB(T2);
+    for (size_t i = 0; i < T1; ++i) rowA[i] = lf[c1[i]] + lf[population - c1[i]];
+    for (size_t j = 0; j < T2; ++j) colB[j] = lf[c2[j]] + lf[population - c2[j]] - lf[population];
+    P.level_log[0] = INFINITY;
+    for (int l = 1; l <= kMaxLevels; ++l) P.level_log[l] = -(double)l * std::log(4.0);
+
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = b.ensure(bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    };
+    CUDA_TRY(up(ctx->d_c1, c1.data(), T1 * 4));
+    CUDA_TRY(up(ctx->d_c2, c2.data(), T2 * 4));
+    CUDA_TRY(up(ctx->d_thr1, thr1, T1 * 4));
+    CUDA_TRY(up(ctx->d_thr2, thr2, T2 * 4));
+    CUDA_TRY(up(ctx->d_lf, lf.data(), lf.size() * 8));
+    CUDA_TRY(up(ctx->d_rowA, rowA.data(), T1 * 8));
+    CUDA_TRY(up(ctx->d_colB, colB.data(), T2 * 8));
+    CUDA_TRY(up(ctx->d_dslot2, dslot2.data(), dslot2.size() * 2));
+    CUDA_TRY(up(ctx->d_bin1, bin1.data(), bin1.size() * 2));
+    CUDA_TRY(up(ctx->d_bin2, bin2.data(), bin2.size() * 2));
+    CUDA_TRY(up(ctx->d_slot2, slot2_of_1, n1 * 4));  // n1 >= 1 here (T1 >= 1)
+    CUDA_TRY(ctx->d_kcrit.ensure((size_t)(P.levels + 1) * T1 * P.T2pad * 2));
+    P.c1 = ctx->d_c1.as<uint32_t>();
+    P.c2 = ctx->d_c2.as<uint32_t>();
+    P.thr1 = ctx->d_thr1.as<uint32_t>();
+    P.thr2 = ctx->d_thr2.as<uint32_t>();
+    P.lf = ctx->d_lf.as<double>();
+    P.rowA = ctx->d_rowA.as<double>();
+    P.colB = ctx->d_colB.as<double>();
+    P.kcrit = ctx->d_kcrit.as<uint16_t>();
+    P.dslot2 = ctx->d_dslot2.as<uint16_t>();
+    P.bin1 = ctx->d_bin1.as<uint16_t>();
+    P.bin2 = ctx->d_bin2.as<uint16_t>();
+    P.slot2_of_1 = ctx->d_slot2.as<int32_t>();
+    CUDA_TRY(launch_build_kcrit(P, ctx->d_kcrit.as<uint16_t>(), ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    ctx->P = P;
+    ctx->has_problem = true;
+    return DTO_B200_OK;
+}
+
+int dto_b200_run_unpermuted(dto_b200_ctx *ctx, dto_b200_record *record_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if (!record_out) return fail(DTO_B200_ERR_INVALID, "null record_out");
+    const Problem &P = ctx->P;
+    CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
+    CUDA_TRY(launch_compose(P, nullptr, nullptr, 1, nullptr, ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    ctx->stats.last_scan_kernel_ms = 0;
+    ctx->stats.last_sigma_kernel_ms = 0;
+    ctx->stats.last_scan_launches = 0;
+    rc = run_tasks(ctx, 1, 0u);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(record_out, ctx->d_records.p, sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
+    return DTO_B200_OK;
+}
+
+int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t *perm2, size_t Pn,
+                                  dto_b200_record *records_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if (Pn == 0) return DTO_B200_OK;
+    if (!perm1 || !perm2 || !records_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    const Problem &P = ctx->P;
+    // bound the staging footprint to ~512 MiB of indices per batch
+    const size_t per_task = ((size_t)P.n1 + P.n2 + std::max(P.n1, P.n2)) * 4 + (size_t)P.pb_stride * 2;
+    size_t batch = std::max<size_t>(1, ((size_t)512 << 20) / per_task);
+    batch = std::min(batch, (size_t)auto_batch(ctx));
+    ctx->stats.last_scan_kernel_ms = 0;
+    ctx->stats.last_sigma_kernel_ms = 0;
+    ctx->stats.last_scan_launches = 0;
+    for (size_t done = 0; done < Pn; done += batch) {
+        const int n = (int)std::min(batch, Pn - done);
+        CUDA_TRY(ctx->d_perm1.ensure((size_t)n * P.n1 * 4));
+        CUDA_TRY(ctx->d_perm2.ensure((size_t)n * P.n2 * 4));
+        CUDA_TRY(ctx->d_inv.ensure((size_t)n * std::max(P.n1, P.n2) * 4));
+        CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_perm1.p, perm1 + done * P.n1, (size_t)n * P.n1 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_perm2.p, perm2 + done * P.n2, (size_t)n * P.n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
+        CUDA_TRY(launch_compose(P, ctx->d_perm1.as<uint32_t>(), ctx->d_perm2.as<uint32_t>(), n, ctx->d_inv.as<uint32_t>(),
+                                ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
+        ctx->stats.kernel_launches += 5;
+        int err = 0;
+        CUDA_TRY(cudaMemcpyAsync(&err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (err) return fail(DTO_B200_ERR_INVALID, "perm1/perm2 rows must each be a permutation of 0..n-1");
+        rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpy(records_out + done, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
+    }
+    return DTO_B200_OK;
+}
+
+static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, size_t Pn, dto_b200_record *h_records,
+                             double *h_minp, dto_b200_record *d_records_out, double *d_minp_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if (Pn == 0) return DTO_B200_OK;
+    const Problem &P = ctx->P;
+    const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
+    if (sigma_smem_bytes(P, B1, B2) > ctx->smem_optin)
+        return fail(DTO_B200_ERR_UNSUPPORTED,
+                    "pairing kernel needs %zu B of shared memory (> %zu): lists this long are not supported yet",
+                    sigma_smem_bytes(P, B1, B2), ctx->smem_optin);
+    const size_t batch = (size_t)auto_batch(ctx);
+    ctx->stats.last_scan_kernel_ms = 0;
+    ctx->stats.last_sigma_kernel_ms = 0;
+    ctx->stats.last_scan_launches = 0;
+    if (h_records || h_minp) CUDA_TRY(ctx->h_records.ensure(std::min(batch, Pn) * sizeof(dto_b200_record)));
+    for (size_t done = 0; done < Pn; done += batch) {
+        const int n = (int)std::min(batch, Pn - done);
+        CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+        CUDA_TRY(launch_sigma_sort(P, seed, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr,
+                                   std::min(n, ctx->sm_count * 4), ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
+        if (rc) return rc;
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        ctx->stats.last_sigma_kernel_ms += ms;
+        if (h_records || h_minp) {
+            dto_b200_record *stage = ctx->h_records.as<dto_b200_record>();
+            CUDA_TRY(cudaMemcpyAsync(stage, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (h_records) memcpy(h_records + done, stage, (size_t)n * sizeof(dto_b200_record));
+            if (h_minp)
+                for (int t = 0; t < n; ++t) h_minp[done + t] = stage[t].pvalue;
+        }
+        if (d_records_out)
+            CUDA_TRY(cudaMemcpyAsync(d_records_out + done, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (d_minp_out)
+            CUDA_TRY(cudaMemcpy2DAsync(d_minp_out + done, sizeof(double),
+                                       reinterpret_cast<const char *>(ctx->d_records.p) + offsetof(dto_b200_record, pvalue),
+                                       sizeof(dto_b200_record), sizeof(double), (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (d_records_out || d_minp_out) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return DTO_B200_OK;
+}
+
+int dto_b200_run_permuted_philox(dto_b200_ctx *ctx, uint64_t seed, uint64_t first_perm_id, size_t Pn,
+                                 dto_b200_record *records_out, double *minp_out) {
+    return run_philox_common(ctx, seed, first_perm_id, Pn, records_out, minp_out, nullptr, nullptr);
+}
+
+int dto_b200_run_permuted_philox_device(dto_b200_ctx *ctx, uint64_t seed, uint64_t first_perm_id, size_t Pn,
+                                        double *d_minp_out, dto_b200_record *d_records_out) {
+    return run_philox_common(ctx, seed, first_perm_id, Pn, nullptr, nullptr, d_records_out, d_minp_out);
+}
+
+int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, uint32_t *pos2_of_pos1_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if (!pos2_of_pos1_out) return fail(DTO_B200_ERR_INVALID, "null output");
+    const Problem &P = ctx->P;
+    const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
+    if (sigma_smem_bytes(P, B1, B2) > ctx->smem_optin)
+        return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel does not fit shared memory");
+    CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
+    CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_pair.p, 0xFF, (size_t)(P.n1 ? P.n1 : 1) * 4, ctx->stream));
+    CUDA_TRY(launch_sigma_sort(P, seed, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), 1, ctx->stream));
+    ctx->stats.kernel_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(pos2_of_pos1_out, ctx->d_pair.p, (size_t)P.n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DTO_B200_OK;
+}
+
+int dto_b200_grid_debug(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t *perm2, uint32_t *overlap_out,
+                        double *pvalue_out, double *logp_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if ((perm1 == nullptr) != (perm2 == nullptr))
+        return fail(DTO_B200_ERR_INVALID, "perm1 and perm2 must both be given or both be NULL");
+    const Problem &P = ctx->P;
+    const size_t cells = (size_t)P.T1 * P.T2;
+    CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
+    CUDA_TRY(ctx->d_H.ensure(cells * 4));
+    CUDA_TRY(ctx->d_pv.ensure(cells * 8));
+    CUDA_TRY(ctx->d_logp.ensure(cells * 8));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
+    if (perm1) {
+        CUDA_TRY(ctx->d_perm1.ensure((size_t)P.n1 * 4));
+        CUDA_TRY(ctx->d_perm2.ensure((size_t)P.n2 * 4));
+        CUDA_TRY(ctx->d_inv.ensure((size_t)std::max(P.n1, P.n2) * 4));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_perm1.p, perm1, (size_t)P.n1 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_perm2.p, perm2, (size_t)P.n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(launch_compose(P, perm1 ? ctx->d_perm1.as<uint32_t>() : nullptr, perm2 ? ctx->d_perm2.as<uint32_t>() : nullptr,
+                            1, ctx->d_inv.as<uint32_t>(), ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (err) return fail(DTO_B200_ERR_INVALID, "perm1/perm2 must each be a permutation of 0..n-1");
+    CUDA_TRY(launch_full_grid(P, ctx->d_pb.as<uint16_t>(), ctx->d_H.as<uint32_t>(), pvalue_out ? ctx->d_pv.as<double>() : nullptr,
+                              logp_out ? ctx->d_logp.as<double>() : nullptr, ctx->stream));
+    ctx->stats.kernel_launches += 5;
+    if (overlap_out) CUDA_TRY(cudaMemcpyAsync(overlap_out, ctx->d_H.p, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pvalue_out) CUDA_TRY(cudaMemcpyAsync(pvalue_out, ctx->d_pv.p, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (logp_out) CUDA_TRY(cudaMemcpyAsync(logp_out, ctx->d_logp.p, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return DTO_B200_OK;
+}
+
+int dto_b200_hypergeometric_pvalues(dto_b200_ctx *ctx, const uint64_t *N, const uint64_t *K, const uint64_t *n,
+                                    const uint64_t *k, size_t count, double *pvalue_out) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (count == 0) return DTO_B200_OK;
+    if (!N || !K || !n || !k || !pvalue_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    uint64_t maxN = 0;
+    for (size_t x = 0; x < count; ++x) maxN = std::max(maxN, N[x]);
+    if (maxN > ((uint64_t)1 << 27)) return fail(DTO_B200_ERR_UNSUPPORTED, "population exceeds 2^27");
+    std::vector<double> lf;
+    host_fill_ln_factorial(lf, maxN);
+    DevBuf d_lf, d_in, d_out;
+    CUDA_TRY(d_lf.ensure(lf.size() * 8));
+    CUDA_TRY(d_in.ensure(count * 8 * 4));
+    CUDA_TRY(d_out.ensure(count * 8));
+    uint64_t *din = d_in.as<uint64_t>();
+    CUDA_TRY(cudaMemcpy(d_lf.p, lf.data(), lf.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(din, N, count * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(din + count, K, count * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(din + 2 * count, n, count * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(din + 3 * count, k, count * 8, cudaMemcpyHostToDevice));
+    cudaError_t e = launch_pvalues(d_lf.as<double>(), din, din + count, din + 2 * count, din + 3 * count, count,
+                                   d_out.as<double>(), ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(pvalue_out, d_out.p, count * 8, cudaMemcpyDeviceToHost);
+    d_lf.release();
+    d_in.release();
+    d_out.release();
+    ctx->stats.kernel_launches += 1;
+    CUDA_TRY(e);
+    return DTO_B200_OK;
+}
+
+int dto_b200_probe_fp64_tflops(dto_b200_ctx *ctx, double *tflops_out) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!tflops_out) return fail(DTO_B200_ERR_INVALID, "null output");
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
+    DevBuf out;
+    CUDA_TRY(out.ensure((size_t)blocks * threads * 8));
+    CUDA_TRY(launch_fp64_probe(out.as<double>(), blocks, threads, 64, ctx->stream));  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CUDA_TRY(launch_fp64_probe(out.as<double>(), blocks, threads, iters, ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        const double flops = (double)blocks * threads * (double)iters * 8.0 * 2.0;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    out.release();
+    *tflops_out = best;
+    return DTO_B200_OK;
+}
+
+int dto_b200_probe_hbm_gbs(dto_b200_ctx *ctx, double *gbs_out) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!gbs_out) return fail(DTO_B200_ERR_INVALID, "null output");
+    const size_t bytes = (size_t)1 << 30;
+    DevBuf a, b;
+    CUDA_TRY(a.ensure(bytes));
+    CUDA_TRY(b.ensure(bytes));
+    CUDA_TRY(cudaMemsetAsync(a.p, 1, bytes, ctx->stream));
+    CUDA_TRY(launch_hbm_probe(a.p, b.p, bytes, ctx->sm_count * 16, ctx->stream));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
+        CUDA_TRY(launch_hbm_probe(a.p, b.p, bytes, ctx->sm_count * 16, ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        best = std::max(best, 2.0 * (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    a.release();
+    b.release();
+    *gbs_out = best;
+    return DTO_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,427 @@
+// dto_host.cpp -- host layer mirroring the reference crate's public surface above the CUDA engine:
+// collections (RankedFeatureList::from, thresholds), readers, compute_population_size, the string-id ->
+// slot canonicalisation, run_single_node's task sharding (threads/MPI ranks -> GPUs), and the exact host
+// epilogue (empirical_pvalue, fdr, serde_json-style pretty printing).
+// Compile with -ffp-contract=off: generate_thresholds and fdr must round like rustc's f64 code.
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "dto_internal.hpp"
+
+using dto::fail;
+
+struct dto_b200_ranked_list {
+    std::vector<std::string> ids;      // sorted by rank (stable)
+    std::vector<uint32_t> ranks;       // ascending
+    std::vector<uint32_t> thresholds;  // src/collections/ranked.rs:359-375
+};
+
+struct dto_b200_feature_list {
+    std::vector<std::string> ids;
+};
+
+namespace {
+
+std::string trim_ws(const std::string &s) {
+    size_t b = 0, e = s.size();
+    auto ws = [](unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); };
+    while (b < e && ws((unsigned char)s[b])) ++b;
+    while (e > b && ws((unsigned char)s[e - 1])) --e;
+    return s.substr(b, e - b);
+}
+
+// BufRead::lines(): split on '\n', drop one trailing '\r'
+bool read_lines(const char *path, std::vector<std::string> &out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        out.push_back(line);
+    }
+    return true;
+}
+
+// generate_thresholds (src/collections/ranked.rs:359-375).  T1 = 1, T_n = floor(T_{n-1} * 1.01 + 1) while
+// <= max rank.  The reference's "set the final threshold to the maximum rank" statement mutates the previous
+// (empty) vector and is a no-op, so the series is NOT closed with max_rank; reproduced on purpose.
+void generate_thresholds(const std::vector<uint32_t> &sorted_ranks, std::vector<uint32_t> &out) {
+    out.clear();
+    const uint32_t max_rank = sorted_ranks.empty() ? 0u : sorted_ranks.back();
+    uint32_t current = 1;
+    while (current <= max_rank) {
+        out.push_back(current);
+        const double next = std::floor((double)current * 1.01 + 1.0);
+        if (next >= 4294967295.0) break;  // `as u32` saturates; the reference would spin forever here
+        current = (uint32_t)next;
+    }
+}
+
+// serde_json prints f64 with ryu: shortest round-trip digits, decimal notation for 1e-5 <= |v| < 1e16
+std::string format_f64(double v) {
+    if (!std::isfinite(v)) return "null";  // serde_json maps non-finite floats to null
+    if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[64];
+    auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    std::string s(buf, res.ptr);
+    std::string out;
+    size_t pos = 0;
+    if (s[0] == '-') {
+        out = "-";
+        pos = 1;
+    }
+    const size_t epos = s.find('e', pos);
+    std::string mant = s.substr(pos, epos - pos);
+    const int e10 = std::stoi(s.substr(epos + 1));
+    std::string digits;
+    for (char c : mant)
+        if (c != '.') digits.push_back(c);
+    const int length = (int)digits.size();
+    const int k = e10 - (length - 1);
+    const int kk = length + k;
+    if (k >= 0 && kk <= 16) {
+        out += digits + std::string((size_t)k, '0') + ".0";
+    } else if (kk > 0 && kk <= 16) {
+        out += digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+    } else if (kk > -5 && kk <= 0) {
+        out += "0." + std::string((size_t)(-kk), '0') + digits;
+    } else if (length == 1) {
+        out += digits + "e" + std::to_string(kk - 1);
+    } else {
+        out += digits.substr(0, 1) + "." + digits.substr(1) + "e" + std::to_string(kk - 1);
+    }
+    return out;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------
+// collections
+// ---------------------------------------------------------------------------------------------------
+int dto_b200_ranked_list_from(const char *const *ids, const uint32_t *ranks, size_t n, dto_b200_ranked_list **out) {
+    if (!out) return fail(DTO_B200_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (n && (!ids || !ranks)) return fail(DTO_B200_ERR_INVALID, "null ids/ranks");
+    auto *l = new dto_b200_ranked_list();
+    // sort_genes_and_ranks (ranked.rs:527-542): stable sort_by_key on rank
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ranks[a] < ranks[b]; });
+    l->ids.reserve(n);
+    l->ranks.reserve(n);
+    for (uint32_t o : order) {
+        if (!ids[o]) {
+            delete l;
+            return fail(DTO_B200_ERR_INVALID, "null feature id at index %u", o);
+        }
+        l->ids.emplace_back(ids[o]);
+        l->ranks.push_back(ranks[o]);
+    }
+    generate_thresholds(l->ranks, l->thresholds);
+    *out = l;
+    return DTO_B200_OK;
+}
+
+int dto_b200_read_ranked_list_csv(const char *path, dto_b200_ranked_list **out) {
+    if (!path || !out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    std::vector<std::string> lines;
+    if (!read_lines(path, lines)) return fail(DTO_B200_ERR_IO, "Could not open file: %s", path);
+    std::vector<std::string> ids;
+    std::vector<uint32_t> ranks;
+    for (size_t i = 0; i < lines.size(); ++i) {
+        const std::string &line = lines[i];
+        // fields = line.split(','); exactly two fields or panic (read_ranked_feature_list_from_csv.rs:58-61)
+        const size_t c = line.find(',');
+        if (c == std::string::npos || line.find(',', c + 1) != std::string::npos)
+            return fail(DTO_B200_ERR_PANIC, "Invalid format in file %s at line %zu", path, i + 1);
+        const std::string f = trim_ws(line.substr(0, c));
+        std::string r = trim_ws(line.substr(c + 1));
+        // usize::from_str: optional '+', then decimal digits only
+        size_t b = (!r.empty() && r[0] == '+') ? 1 : 0;
+        if (b >= r.size()) return fail(DTO_B200_ERR_PANIC, "Invalid rank value: \"%s\" (%s line %zu)", r.c_str(), path, i + 1);
+        unsigned long long v = 0;
+        for (size_t x = b; x < r.size(); ++x) {
+            if (r[x] < '0' || r[x] > '9')
+                return fail(DTO_B200_ERR_PANIC, "Invalid rank value: \"%s\" (%s line %zu)", r.c_str(), path, i + 1);
+            if (v > (0xFFFFFFFFFFFFFFFFull - (unsigned)(r[x] - '0')) / 10ull)
+                return fail(DTO_B200_ERR_PANIC, "Invalid rank value: \"%s\" (%s line %zu)", r.c_str(), path, i + 1);
+            v = v * 10ull + (unsigned)(r[x] - '0');
+        }
+        ids.push_back(f);
+        ranks.push_back((uint32_t)v);  // `rank as u32` truncates (:65)
+    }
+    std::vector<const char *> cids(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) cids[i] = ids[i].c_str();
+    return dto_b200_ranked_list_from(cids.data(), ranks.data(), ids.size(), out);
+}
+
+void dto_b200_ranked_list_free(dto_b200_ranked_list *l) { delete l; }
+size_t dto_b200_ranked_list_len(const dto_b200_ranked_list *l) { return l ? l->ids.size() : 0; }
+size_t dto_b200_ranked_list_num_thresholds(const dto_b200_ranked_list *l) { return l ? l->thresholds.size() : 0; }
+const uint32_t *dto_b200_ranked_list_thresholds(const dto_b200_ranked_list *l) { return l ? l->thresholds.data() : nullptr; }
+const uint32_t *dto_b200_ranked_list_ranks(const dto_b200_ranked_list *l) { return l ? l->ranks.data() : nullptr; }
+const char *dto_b200_ranked_list_id(const dto_b200_ranked_list *l, size_t i) {
+    return (l && i < l->ids.size()) ? l->ids[i].c_str() : nullptr;
+}
+
+int dto_b200_feature_list_from(const char *const *ids, size_t n, dto_b200_feature_list **out) {
+    if (!out || (n && !ids)) return fail(DTO_B200_ERR_INVALID, "null argument");
+    auto *l = new dto_b200_feature_list();
+    for (size_t i = 0; i < n; ++i) l->ids.emplace_back(ids[i] ? ids[i] : "");
+    *out = l;
+    return DTO_B200_OK;
+}
+
+int dto_b200_read_feature_list(const char *path, dto_b200_feature_list **out) {
+    if (!path || !out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    *out = nullptr;
+    std::vector<std::string> lines;
+    if (!read_lines(path, lines)) return fail(DTO_B200_ERR_IO, "Could not open file: %s", path);
+    auto *l = new dto_b200_feature_list();
+    for (auto &s : lines) l->ids.push_back(trim_ws(s));  // every line counts, blank ones too (:48-52)
+    *out = l;
+    return DTO_B200_OK;
+}
+
+void dto_b200_feature_list_free(dto_b200_feature_list *l) { delete l; }
+size_t dto_b200_feature_list_len(const dto_b200_feature_list *l) { return l ? l->ids.size() : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// compute_population_size (src/dto/compute_population_size.rs:66-104)
+// ---------------------------------------------------------------------------------------------------
+int dto_b200_compute_population_size(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2,
+                                     const dto_b200_feature_list *background, uint64_t *population_out) {
+    if (!l1 || !l2 || !population_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    if (!background) {
+        std::unordered_set<std::string> s2(l2->ids.begin(), l2->ids.end());
+        size_t inter = 0;  // FeatureList::intersect keeps list-1 items whose id is in list 2 (feature_list.rs:278-286)
+        for (auto &g : l1->ids) inter += s2.count(g);
+        if (inter != l1->ids.size() || inter != l2->ids.size())
+            return fail(DTO_B200_ERR_PANIC, "If no background is provided, the feature lists must have identical genes.");
+        *population_out = inter;
+        return DTO_B200_OK;
+    }
+    std::unordered_set<std::string> bg(background->ids.begin(), background->ids.end());
+    const dto_b200_ranked_list *lists[2] = {l1, l2};
+    const char *names[2] = {"first", "second"};
+    for (int w = 0; w < 2; ++w) {
+        std::string missing;
+        for (auto &g : lists[w]->ids)
+            if (!bg.count(g)) {
+                if (!missing.empty()) missing += ", ";
+                missing += "\"" + g + "\"";
+                if (missing.size() > 600) {
+                    missing += ", ...";
+                    break;
+                }
+            }
+        if (!missing.empty())
+            return fail(DTO_B200_ERR_PANIC, "The following genes in the %s ranked feature list are not in the background: [%s]",
+                        names[w], missing.c_str());
+    }
+    *population_out = background->ids.size();  // lines are counted as-is, duplicates and blanks included (:101)
+    return DTO_B200_OK;
+}
+
+// string ids -> slot map (the integer form of intersect_genes.rs:38-56)
+int dto_b200_load_lists(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2,
+                        uint64_t population) {
+    if (!ctx || !l1 || !l2) return fail(DTO_B200_ERR_INVALID, "null argument");
+    std::unordered_map<std::string, int32_t> pos2;
+    pos2.reserve(l2->ids.size() * 2);
+    for (size_t j = 0; j < l2->ids.size(); ++j)
+        if (!pos2.emplace(l2->ids[j], (int32_t)j).second)
+            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list", l2->ids[j].c_str());
+    std::unordered_set<std::string> seen1;
+    seen1.reserve(l1->ids.size() * 2);
+    std::vector<int32_t> slot(l1->ids.size(), -1);
+    for (size_t a = 0; a < l1->ids.size(); ++a) {
+        if (!seen1.insert(l1->ids[a]).second)
+            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list", l1->ids[a].c_str());
+        auto it = pos2.find(l1->ids[a]);
+        if (it != pos2.end()) slot[a] = it->second;
+    }
+    return dto_b200_set_problem(ctx, l1->ranks.data(), l1->ranks.size(), l1->thresholds.data(), l1->thresholds.size(),
+                                l2->ranks.data(), l2->ranks.size(), l2->thresholds.data(), l2->thresholds.size(),
+                                slot.data(), population);
+}
+
+int dto_b200_optimize(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, int permute,
+                      uint64_t population, uint64_t seed, uint64_t perm_id, dto_b200_record *record_out) {
+    if (!record_out) return fail(DTO_B200_ERR_INVALID, "null record_out");
+    int rc = dto_b200_load_lists(ctx, l1, l2, population);
+    if (rc) return rc;
+    if (!permute) return dto_b200_run_unpermuted(ctx, record_out);
+    return dto_b200_run_permuted_philox(ctx, seed, perm_id, 1, record_out, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// run_single_node (src/run/single_node.rs:83-137) -- tasks sharded over GPUs instead of threads / MPI ranks
+// ---------------------------------------------------------------------------------------------------
+int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, uint64_t population,
+                             const uint8_t *task_permute, size_t n_tasks, const int *devices, size_t n_devices,
+                             uint64_t seed, dto_b200_record *records_out) {
+    if (!l1 || !l2) return fail(DTO_B200_ERR_INVALID, "null list");
+    if (n_tasks == 0) return DTO_B200_OK;
+    if (!task_permute || !records_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    std::vector<int> devs;
+    if (n_devices == 0 || !devices) devs.push_back(0);
+    else devs.assign(devices, devices + n_devices);
+
+    // runs of consecutive permuted task ids, so each maps onto one philox id range
+    struct Run {
+        size_t first, count;
+    };
+    std::vector<Run> runs;
+    std::vector<size_t> unperm;
+    size_t n_perm = 0;
+    for (size_t t = 0; t < n_tasks; ++t) {
+        if (!task_permute[t]) {
+            unperm.push_back(t);
+            continue;
+        }
+        ++n_perm;
+        if (!runs.empty() && runs.back().first + runs.back().count == t) runs.back().count++;
+        else runs.push_back({t, 1});
+    }
+    // contiguous, near-equal shards of the permuted tasks per device (multi_node.rs:114-129 chunks by rank the same way)
+    const size_t G = devs.size();
+    std::vector<std::vector<Run>> shard(G);
+    {
+        const size_t per = (n_perm + G - 1) / G;
+        size_t g = 0, room = per;
+        for (Run r : runs) {
+            while (r.count) {
+                if (room == 0) {
+                    ++g;
+                    room = per;
+                }
+                const size_t take = std::min(room, r.count);
+                shard[g].push_back({r.first, take});
+                r.first += take;
+                r.count -= take;
+                room -= take;
+            }
+        }
+    }
+    std::vector<int> rcs(G, DTO_B200_OK);
+    std::vector<std::string> errs(G);
+    auto worker = [&](size_t g) {
+        const bool has_work = !shard[g].empty() || (g == 0 && !unperm.empty());
+        if (!has_work) return;
+        dto_b200_ctx *ctx = nullptr;
+        int rc = dto_b200_create(&ctx, devs[g]);
+        if (rc == DTO_B200_OK) rc = dto_b200_load_lists(ctx, l1, l2, population);
+        if (rc == DTO_B200_OK && g == 0 && !unperm.empty()) {
+            dto_b200_record r;
+            rc = dto_b200_run_unpermuted(ctx, &r);
+            if (rc == DTO_B200_OK)
+                for (size_t t : unperm) records_out[t] = r;
+        }
+        for (size_t x = 0; rc == DTO_B200_OK && x < shard[g].size(); ++x)
+            rc = dto_b200_run_permuted_philox(ctx, seed, (uint64_t)shard[g][x].first, shard[g][x].count,
+                                              records_out + shard[g][x].first, nullptr);
+        if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
+        rcs[g] = rc;
+        dto_b200_destroy(ctx);
+    };
+    if (G == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) th.emplace_back(worker, g);
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; ++g)
+        if (rcs[g] != DTO_B200_OK) return fail(rcs[g], "device %d: %s", devs[g], errs[g].c_str());
+    return DTO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue: fdr (src/stat_operations/fdr.rs:29-60), empirical_pvalue (src/stat_operations/empirical_pvalue.rs:109-187)
+// ---------------------------------------------------------------------------------------------------
+int dto_b200_fdr(uint64_t list1_len, uint64_t list2_len, uint64_t overlap, uint64_t population, double sensitivity,
+                 double *fdr_out) {
+    if (!fdr_out) return fail(DTO_B200_ERR_INVALID, "null fdr_out");
+    if (sensitivity <= 0.0) return fail(DTO_B200_ERR_PANIC, "Sensitivity must be greater than 0.");
+    const double df = std::fmax((double)overlap / sensitivity, 0.0);
+    const double b = std::fmax((double)list1_len - df, 0.0);
+    const double r = std::fmax((double)list2_len - df, 0.0);
+    const double num = b * r;
+    const double den = (double)population * (double)overlap;
+    *fdr_out = den > 0.0 ? num / den : 0.0;
+    return DTO_B200_OK;
+}
+
+int dto_b200_empirical_pvalue(const dto_b200_record *records, size_t n, dto_b200_final_result *out) {
+    if (!out || (n && !records)) return fail(DTO_B200_ERR_INVALID, "null argument");
+    const dto_b200_record *unperm = nullptr;
+    size_t n_unperm = 0, n_perm = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (records[i].flags & DTO_B200_FLAG_PERMUTED) {
+            ++n_perm;
+        } else {
+            if (!unperm) unperm = &records[i];
+            ++n_unperm;
+        }
+    }
+    if (n_unperm != 1)
+        fprintf(stderr, "Warning: Expected exactly one unpermuted result, but found %zu.\n", n_unperm);
+    if (!unperm) return fail(DTO_B200_ERR_PANIC, "No unpermuted result found in the provided results.");
+    out->rank1 = unperm->rank1;
+    out->rank2 = unperm->rank2;
+    out->set1_len = unperm->set1_len;
+    out->set2_len = unperm->set2_len;
+    out->population_size = unperm->population_size;
+    out->unpermuted_intersection_size = unperm->intersection_size;
+    out->unpermuted_pvalue = unperm->pvalue;
+    int rc = dto_b200_fdr(unperm->set1_len, unperm->set2_len, unperm->intersection_size, unperm->population_size, 0.8,
+                          &out->fdr);
+    if (rc) return rc;
+    if (n_perm == 0) {
+        out->empirical_pvalue = 1.0;
+        return DTO_B200_OK;
+    }
+    size_t c = 0;
+    for (size_t i = 0; i < n; ++i)
+        if ((records[i].flags & DTO_B200_FLAG_PERMUTED) && records[i].pvalue <= unperm->pvalue) ++c;
+    out->empirical_pvalue = (double)c / (double)n_perm;  // no +1 correction (:160-165)
+    return DTO_B200_OK;
+}
+
+int dto_b200_final_result_json(const dto_b200_final_result *r, char *buf, size_t cap, size_t *len_out) {
+    if (!r) return fail(DTO_B200_ERR_INVALID, "null result");
+    std::string s = "{\n";
+    s += "  \"empirical_pvalue\": " + format_f64(r->empirical_pvalue) + ",\n";
+    s += "  \"fdr\": " + format_f64(r->fdr) + ",\n";
+    s += "  \"population_size\": " + std::to_string(r->population_size) + ",\n";
+    s += "  \"rank1\": " + std::to_string(r->rank1) + ",\n";
+    s += "  \"rank2\": " + std::to_string(r->rank2) + ",\n";
+    s += "  \"set1_len\": " + std::to_string(r->set1_len) + ",\n";
+    s += "  \"set2_len\": " + std::to_string(r->set2_len) + ",\n";
+    s += "  \"unpermuted_intersection_size\": " + std::to_string(r->unpermuted_intersection_size) + ",\n";
+    s += "  \"unpermuted_pvalue\": " + format_f64(r->unpermuted_pvalue) + "\n";
+    s += "}";
+    if (len_out) *len_out = s.size();
+    if (buf && cap) {
+        const size_t ncopy = std::min(cap - 1, s.size());
+        memcpy(buf, s.data(), ncopy);
+        buf[ncopy] = '\0';
+    }
+    return DTO_B200_OK;
+}
+
+}  // extern "C"

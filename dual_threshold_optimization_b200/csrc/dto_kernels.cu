@@ -1,0 +1,833 @@
+// dto_kernels.cu -- hand-written sm_100a kernels of the DTO hot path.
+//
+//   K0  sigma_sort_kernel      one CTA per permutation: exactly-uniform random pairing of list-1 and list-2
+//                              positions (Philox keys, shared-memory bucket sort), emitted as the row-histogram
+//                              slot of every list-1 position's partner            (collections/permuted.rs:56-60,90-101)
+//   K0' compose_pairing_kernel same output from HOST-supplied perm1/perm2 (parity mode)
+//   K1  scan_kernel            one WARP per permutation: row-streamed histogram (shared-memory atomics) ->
+//                              2-D inclusive prefix sum in registers/shuffles -> critical-overlap screen ->
+//                              statrs-order FP64 tail for the few surviving cells -> warp-shuffle argmin with the
+//                              reference tie-break        (process_threshold_pairs.rs:84-128, optimize_main.rs:73-116)
+//   K2  build_kcrit_kernel     per-problem screen tables: smallest k with p(K_i, n_j, k) <= 4^-l
+//   K3  full_* kernels         dense T1 x T2 grid (debug=true analogue, optimize_main.rs:68-70) + exact argmin;
+//                              also the last-resort path for degenerate tasks (min p >= 1)
+#include "dto_kernels.cuh"
+
+namespace dto {
+
+// =====================================================================================================
+// K2: critical-overlap tables
+// =====================================================================================================
+__global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint16_t *__restrict__ kcrit) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= P.T1 * P.T2) return;
+    const int i = cell / P.T2, j = cell % P.T2;
+    const uint64_t N = P.N;
+    const uint64_t K = P.c1[i], n = P.c2[j];
+    const uint64_t lower = (K + n > N) ? (K + n - N) : 0;
+    const uint64_t upper = K < n ? K : n;
+    if (lower + 1 > upper) return;  // no valid k: table stays 0xFFFF
+    const size_t col = (size_t)(j % P.CH) * 32 + (size_t)(j / P.CH);
+    const size_t level_stride = (size_t)P.T1 * P.T2pad;
+    uint16_t *dst = kcrit + (size_t)i * P.T2pad + col;
+    dst[0] = (uint16_t)(lower + 1);  // level 0: every cell the reference does not short-circuit to p = 1
+
+    const double rowA = P.rowA[i], colB = P.colB[j];
+    auto lpmf = [&](uint64_t x) { return log_pmf(P, rowA, colB, (uint32_t)K, (uint32_t)n, (uint32_t)x); };
+    const uint64_t mode = (uint64_t)(((double)(n + 1) * (double)(K + 1)) / (double)(N + 2));
+    uint64_t xs = mode > lower + 1 ? mode : lower + 1;
+    if (xs > upper) xs = upper;
+    int l = P.levels;
+    if (lpmf(xs) < -80.0) {  // the whole valid range is negligible (support starts far above the mode)
+        for (; l >= 1; --l) dst[l * level_stride] = (uint16_t)(lower + 1);
+        return;
+    }
+    uint64_t x_end = upper;
+    if (lpmf(upper) < -80.0) {
+        uint64_t lo = xs, hi = upper;  // lpmf(lo) >= -80 > lpmf(hi), lpmf decreasing above the mode
+        while (hi - lo > 1) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (lpmf(mid) >= -80.0) lo = mid;
+            else hi = mid;
+        }
+        x_end = hi;
+    }
+    uint64_t k = x_end;
+    double t = exp(lpmf(k));
+    double S = 0.0;
+    for (;;) {
+        S += t;  // p(k) up to a tail below e^-80
+        while (l >= 1 && S > exp(P.level_log[l]) * (1.0 + 1e-6)) {
+            dst[l * level_stride] = (k + 1 <= upper) ? (uint16_t)(k + 1) : kNoSlot;
+            --l;
+        }
+        if (l == 0) break;
+        if (k == lower + 1) {
+            for (; l >= 1; --l) dst[l * level_stride] = (uint16_t)(lower + 1);
+            break;
+        }
+        // pmf(k-1) = pmf(k) * k (N-K-n+k) / ((K-k+1)(n-k+1))
+        t *= ((double)k * (double)(N - K - n + k)) / ((double)(K - k + 1) * (double)(n - k + 1));
+        --k;
+    }
+}
+
+// =====================================================================================================
+// K0: exactly-uniform random pairing by sorting Philox keys in shared memory.
+//   key(e) = 32 random bits; elements are bucketed by the top B bits (histogram + exclusive scan + scatter with
+//   shared-memory atomics), then ranked inside their bucket (~8 members) on (next 16 key bits, secondary Philox
+//   key on ties, index) -- a total order, so the result does not depend on the order atomics resolve in.
+// =====================================================================================================
+struct SortShared {
+    uint32_t *words;   // [n]     (rem16 << 16) | element
+    uint32_t *off;     // [NB+1]  bucket offsets (exclusive scan of the histogram)
+    uint32_t *cursor;  // [NB]
+    uint32_t *scan_tmp;  // [32]
+};
+
+__device__ __forceinline__ void philox_keys(uint32_t (&out)[4], uint64_t seed, uint64_t perm_id, uint32_t stream,
+                                            uint32_t block4) {
+    out[0] = block4;
+    out[1] = stream;
+    out[2] = (uint32_t)perm_id;
+    out[3] = (uint32_t)(perm_id >> 32);
+    philox4x32_10(out, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ uint32_t secondary_key(uint64_t seed, uint64_t perm_id, uint32_t stream, uint32_t e) {
+    uint32_t c[4];
+    philox_keys(c, seed, perm_id, stream + 8u, e >> 2);
+    return c[e & 3u];
+}
+
+// exclusive scan of a[0..len) in place, a[len] = total; blockDim.x threads
+__device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t per = (len + nt - 1) / nt;
+    const uint32_t b = tid * per, e = (b + per < len) ? b + per : len;
+    uint32_t sum = 0;
+    for (uint32_t x = b; x < e; ++x) sum += a[x];
+    const uint32_t lane = tid & 31, w = tid >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= (uint32_t)o) inc += v;
+    }
+    if (lane == 31) tmp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = (lane < (nt >> 5)) ? tmp[lane] : 0, s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(kFull, s, o);
+            if (lane >= (uint32_t)o) s += u;
+        }
+        tmp[lane] = s - v;  // exclusive warp offsets
+    }
+    __syncthreads();
+    uint32_t run = tmp[w] + inc - sum;
+    for (uint32_t x = b; x < e; ++x) {
+        const uint32_t v = a[x];
+        a[x] = run;
+        run += v;
+    }
+    if (tid == nt - 1) a[len] = run;  // the last thread's chunk ends at len (or is empty): run == total
+    __syncthreads();
+}
+
+// Ranks the n elements of one Philox stream; calls emit(e, f): element e has the f-th smallest key.
+template <typename Emit>
+__device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id,
+                                          uint32_t stream, Emit emit) {
+    const uint32_t NB = 1u << B;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t x = tid; x <= NB; x += nt) S.off[x] = 0;
+    __syncthreads();
+    const uint32_t nblk = (n + 3) >> 2;
+    for (uint32_t c = tid; c < nblk; c += nt) {
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = c * 4 + q;
+            if (e < n) atomicAdd(&S.off[key[q] >> (32 - B)], 1u);
+        }
+    }
+    __syncthreads();
+    block_exclusive_scan(S.off, NB, S.scan_tmp);
+    for (uint32_t x = tid; x < NB; x += nt) S.cursor[x] = S.off[x];
+    __syncthreads();
+    for (uint32_t c = tid; c < nblk; c += nt) {
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = c * 4 + q;
+            if (e < n) {
+                const uint32_t pos = atomicAdd(&S.cursor[key[q] >> (32 - B)], 1u);
+                S.words[pos] = (((key[q] >> (16 - B)) & 0xFFFFu) << 16) | e;
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t c = tid; c < nblk; c += nt) {
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = c * 4 + q;
+            if (e < n) {
+                const uint32_t b = key[q] >> (32 - B);
+                const uint32_t rem = (key[q] >> (16 - B)) & 0xFFFFu;
+                const uint32_t lo = S.off[b], hi = S.off[b + 1];
+                uint32_t rank = 0;
+                uint32_t sec = 0;
+                bool have_sec = false;
+                for (uint32_t x = lo; x < hi; ++x) {
+                    const uint32_t w = S.words[x];
+                    const uint32_t wr = w >> 16, we = w & 0xFFFFu;
+                    if (wr < rem) {
+                        ++rank;
+                    } else if (wr == rem && we != e) {  // 16-bit tie inside the bucket: decide on fresh random bits
+                        if (!have_sec) {
+                            sec = secondary_key(seed, perm_id, stream, e);
+                            have_sec = true;
+                        }
+                        const uint32_t os = secondary_key(seed, perm_id, stream, we);
+                        if (os < sec || (os == sec && we < e)) ++rank;
+                    }
+                }
+                emit(e, lo + rank);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const Problem P, uint64_t seed, uint64_t first_id,
+                                                                   int n_tasks, int B1, int B2,
+                                                                   uint16_t *__restrict__ pb,
+                                                                   uint32_t *__restrict__ pairing_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+    const int Bmax = B1 > B2 ? B1 : B2;
+    SortShared S;
+    S.words = reinterpret_cast<uint32_t *>(smem_raw);
+    S.off = S.words + nmax;
+    S.cursor = S.off + (1u << Bmax) + 1;
+    S.scan_tmp = S.cursor + (1u << Bmax);
+    uint16_t *out = reinterpret_cast<uint16_t *>(S.scan_tmp + 32);  // [pb_stride]
+    uint16_t *order2 = out + P.pb_stride;                           // [n_common] (general mode only)
+    const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+
+    for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const uint64_t perm_id = first_id + (uint64_t)t;
+        for (uint32_t x = tid; x < P.pb_stride; x += nt) out[x] = kNoSlot;
+        __syncthreads();
+        if (identical) {
+            // element = list-2 position e, rank f = the list-1 position it is paired with
+            block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
+                if (f < P.n1_eff) out[f] = P.dslot2[e];
+                if (pairing_out) pairing_out[(size_t)t * P.n1 + f] = e;
+            });
+        } else {
+            // uniform random partial injection: the n_common lowest-keyed positions of each list, matched by rank
+            block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 1u, [&](uint32_t e, uint32_t f) {
+                if (f < P.n_common) order2[f] = (uint16_t)e;
+            });
+            block_rank_by_random_keys(S, P.n1, B1, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
+                uint32_t partner = 0xFFFFFFFFu;
+                if (f < P.n_common) partner = order2[f];
+                if (e < P.n1_eff && partner != 0xFFFFFFFFu) out[e] = P.dslot2[partner];
+                if (pairing_out) pairing_out[(size_t)t * P.n1 + e] = partner;
+            });
+        }
+        __syncthreads();
+        uint16_t *dst = pb + (size_t)t * P.pb_stride;
+        for (uint32_t x = tid; x < P.pb_stride; x += nt) dst[x] = out[x];
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================
+// K0': pairing from host-supplied indices.  Position j of (permuted) list 1 holds the gene of slot perm1[j];
+// that gene sits at slot slot2_of_1[.] of list 2, which the permuted list 2 shows at position inv2[slot].
+// =====================================================================================================
+__global__ void invert_perm_kernel(const uint32_t *__restrict__ perm, uint32_t n, int n_tasks,
+                                   uint32_t *__restrict__ inv, int *__restrict__ err) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n_tasks) return;
+    const size_t t = idx / n;
+    const uint32_t v = perm[idx];
+    if (v >= n) {
+        atomicExch(err, 1);
+        return;
+    }
+    inv[t * n + v] = (uint32_t)(idx - t * n);
+}
+
+__global__ void check_perm_kernel(const uint32_t *__restrict__ perm, uint32_t n, int n_tasks,
+                                  const uint32_t *__restrict__ inv, int *__restrict__ err) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n_tasks) return;
+    const size_t t = idx / n;
+    const uint32_t v = perm[idx];
+    if (v >= n || inv[t * n + v] != (uint32_t)(idx - t * n)) atomicExch(err, 1);  // duplicate entry
+}
+
+__global__ void compose_pairing_kernel(const Problem P, const uint32_t *__restrict__ perm1,
+                                       const uint32_t *__restrict__ inv2, int n_tasks, uint16_t *__restrict__ pb) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)P.pb_stride * n_tasks) return;
+    const size_t t = idx / P.pb_stride;
+    const uint32_t j = (uint32_t)(idx - t * P.pb_stride);
+    uint16_t v = kNoSlot;
+    if (j < P.n1_eff) {
+        const uint32_t slot1 = perm1 ? perm1[t * P.n1 + j] : j;
+        const int32_t slot2 = P.slot2_of_1[slot1];
+        if (slot2 >= 0) {
+            const uint32_t pos2 = inv2 ? inv2[t * P.n2 + (uint32_t)slot2] : (uint32_t)slot2;
+            v = P.dslot2[pos2];
+        }
+    }
+    pb[idx] = v;
+}
+
+// =====================================================================================================
+// K1: scan kernel
+// =====================================================================================================
+struct __align__(16) Cand {
+    uint32_t ij;
+    uint32_t k;
+    double v;  // log lower bound of p while screening, then the exact p
+};
+
+template <int CH, bool WIDE>
+struct ScanLayout {
+    static constexpr int CHP = CH | 1;
+    static constexpr int QCAP = 32 * CH + 32;
+    static constexpr int CAP = WIDE ? 0 : kCandCap;
+    static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
+    static constexpr size_t q_bytes = (size_t)QCAP * 8;
+    static constexpr size_t per_warp = d_bytes + q_bytes + 16 + (size_t)CAP * sizeof(Cand);
+};
+
+__device__ __forceinline__ uint32_t compact_cands(Cand *c, uint32_t n, double theta, int lane) {
+    uint32_t out = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t b = 0; b < n; b += 32) {
+        const uint32_t idx = b + lane;
+        Cand e;
+        bool keep = false;
+        if (idx < n) {
+            e = c[idx];
+            keep = (e.v - kEps <= theta);
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) c[out + __popc(bal & lt)] = e;
+        out += __popc(bal);
+        __syncwarp();
+    }
+    return out;
+}
+
+template <int CH, bool WIDE>
+__global__ void __launch_bounds__(kScanThreads, (WIDE || CH > 32) ? 1 : 2)
+scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__restrict__ task_ids, int n_tasks,
+            uint32_t record_flags, dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
+            Cand *__restrict__ wide_buf, unsigned long long *__restrict__ counters) {
+    using L = ScanLayout<CH, WIDE>;
+    constexpr int CHP = L::CHP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    uint32_t *s_c1 = reinterpret_cast<uint32_t *>(smem_raw);  // [T1] shared by the CTA
+    const size_t c1_bytes = ((size_t)P.T1 * 4 + 15) & ~(size_t)15;
+    unsigned char *wbase = smem_raw + c1_bytes + (size_t)warp * L::per_warp;
+    uint32_t *D = reinterpret_cast<uint32_t *>(wbase);
+    uint32_t *Qij = reinterpret_cast<uint32_t *>(wbase + L::d_bytes);
+    uint32_t *Qk = Qij + L::QCAP;
+    uint32_t *qcnt = Qk + L::QCAP;
+    Cand *cand = WIDE ? wide_buf + (size_t)(blockIdx.x * warps_per_cta + warp) * (size_t)P.T1 * P.T2
+                      : reinterpret_cast<Cand *>(wbase + L::d_bytes + L::q_bytes + 16);
+    const uint32_t cap = WIDE ? (uint32_t)(P.T1 * P.T2) : (uint32_t)L::CAP;
+    const unsigned lt = (1u << lane) - 1u;
+
+    for (int x = threadIdx.x; x < P.T1; x += blockDim.x) s_c1[x] = P.c1[x];
+    __syncthreads();
+
+    for (int t = blockIdx.x * warps_per_cta + warp; t < n_tasks; t += gridDim.x * warps_per_cta) {
+        const uint32_t task = task_ids ? task_ids[t] : (uint32_t)t;
+        const uint16_t *__restrict__ row = pb + (size_t)task * P.pb_stride;
+        for (int x = lane; x < 32 * CHP; x += 32) D[x] = 0;
+        if (lane == 0) *qcnt = 0;
+        __syncwarp();
+
+        uint32_t kcur[CH];
+#pragma unroll
+        for (int m = 0; m < CH; ++m) kcur[m] = 0;
+        uint32_t koff = 0;
+        double theta = CUDART_INF;  // certified: log(min p of the reference) <= theta
+        int level = 0;
+        uint32_t ncand = 0;
+        bool overflow = false;
+        Best zero;  // best cell on the underflow plateau (reference p == 0.0)
+        zero.p = 0.0;
+        zero.k = 0;
+        zero.ij = 0xFFFFFFFFu;
+        unsigned long long n_level2 = 0;
+
+        // drains the queue of cells that passed the critical-overlap screen, 32 at a time
+        auto drain = [&](bool flush) {
+            uint32_t qc = *qcnt;
+            while (qc >= 32 || (flush && qc > 0)) {
+                const uint32_t take = qc < 32 ? qc : 32;
+                const uint32_t start = qc - take;
+                const bool valid = (uint32_t)lane < take;
+                Cand e;
+                e.ij = 0;
+                e.k = 0;
+                e.v = CUDART_INF;
+                double ub = CUDART_INF;
+                bool keep = false;
+                if (valid) {
+                    e.ij = Qij[start + lane];
+                    e.k = Qk[start + lane];
+                    const uint32_t i = e.ij >> 16, j = e.ij & 0xFFFFu;
+                    const uint32_t K = s_c1[i], n = P.c2[j], k = e.k;
+                    const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
+                    const double a = (double)(K - k), b = (double)(n - k);
+                    const double c = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
+                    const double r1 = (a * b) / (c * d);  // pmf(k+1) / pmf(k)
+                    if (r1 < 1.0 && s < kZeroLo) {
+                        // every tail term underflows: the reference's p is exactly 0.0 -> integer tie-break only
+                        Best z;
+                        z.p = 0.0;
+                        z.k = k;
+                        z.ij = e.ij;
+                        if (better(z, zero)) zero = z;
+                        ub = kZeroHi - kEps;
+                    } else {
+                        double lb = s;  // p >= pmf(k)
+                        if (r1 < 1.0) {
+                            ub = s - log1p(-r1);  // ratios fall with k: p <= pmf(k) / (1 - r1)
+                            // ratios over the next mm steps are all >= r_mm: p >= pmf * (1 - r^(mm+1)) / (1 - r)
+                            double mm = floor(1.0 / (1.0 - r1)) + 1.0;
+                            mm = fmin(mm, fmin(a, b));
+                            if (mm >= 1.0) {
+                                const double rm = ((a - mm + 1.0) * (b - mm + 1.0)) / ((c + mm - 1.0) * (d + mm - 1.0));
+                                if (rm > 0.0 && rm < 1.0) lb = s + log((1.0 - exp((mm + 1.0) * log(rm))) / (1.0 - rm));
+                            }
+                        }
+                        e.v = lb;
+                        keep = true;
+                    }
+                }
+                theta = fmin(theta, warp_min(ub + kEps));
+                keep = keep && (e.v - kEps <= theta);
+                const unsigned bal = __ballot_sync(kFull, keep);
+                const uint32_t add = __popc(bal);
+                if (ncand + add > cap) {
+                    ncand = compact_cands(cand, ncand, theta, lane);
+                    if (ncand + add > cap) overflow = true;
+                }
+                if (!overflow) {
+                    if (keep) cand[ncand + __popc(bal & lt)] = e;
+                    ncand += add;
+                }
+                __syncwarp();
+                n_level2 += take;
+                qc = start;
+            }
+            if (lane == 0) *qcnt = qc;
+            __syncwarp();
+            while (level < P.levels && theta <= P.level_log[level + 1]) ++level;
+        };
+
+        uint32_t base = 0, lo = 0;
+        uint32_t cur = row[lane], nxt = row[32 + lane];
+        for (int i = 0; i < P.T1 && !overflow; ++i) {
+            const uint32_t hi = s_c1[i];
+            // critical overlaps of this row at the current screen level (in flight during the scatter)
+            const uint16_t *__restrict__ kr = P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad + lane;
+            uint32_t kc[CH];
+#pragma unroll
+            for (int m = 0; m < CH; ++m) kc[m] = __ldg(kr + m * 32);
+            // (1) bin this row's genes: position -> partner's column slot, privatised per warp
+            while (lo < hi) {
+                if (lo >= base + 32) {
+                    base += 32;
+                    cur = nxt;
+                    nxt = (base + 32 + lane < P.pb_stride) ? row[base + 32 + lane] : (uint32_t)kNoSlot;
+                    continue;
+                }
+                const uint32_t e = hi < base + 32 ? hi : base + 32;
+                const uint32_t pos = base + lane;
+                if (pos >= lo && pos < e && cur != kNoSlot) atomicAdd(&D[cur], 1u);
+                lo = e;
+            }
+            __syncwarp();
+            // (2) 2-D inclusive prefix: lane-local run over its CH columns + warp exclusive scan of lane totals
+            uint32_t run = 0;
+#pragma unroll
+            for (int m = 0; m < CH; ++m) {
+                const uint32_t d = D[lane * CHP + m];
+                D[lane * CHP + m] = 0;
+                run += d;
+                kcur[m] += run;
+            }
+            uint32_t inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += v;
+            }
+            koff += inc - run;
+            // (3) screen: only k >= kcrit can have p <= tau_level
+#pragma unroll
+            for (int m = 0; m < CH; ++m) {
+                const uint32_t k = kcur[m] + koff;
+                if (k >= kc[m]) {
+                    const uint32_t slot = atomicAdd(qcnt, 1u);
+                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + m);
+                    Qk[slot] = k;
+                }
+            }
+            __syncwarp();
+            if (*qcnt >= 32) drain(false);
+        }
+
+        if (overflow) {
+            if (lane == 0) status[task] = 1;  // candidate buffer overflow: re-run with the global buffer
+            __syncwarp();
+            continue;
+        }
+        drain(true);
+        if (overflow) {
+            if (lane == 0) status[task] = 1;
+            __syncwarp();
+            continue;
+        }
+        ncand = compact_cands(cand, ncand, theta, lane);
+
+        // (4) statrs-order FP64 tail for the survivors, one candidate per lane
+        Best best;
+        best.p = CUDART_INF;
+        best.k = 0;
+        best.ij = 0xFFFFFFFFu;
+        for (uint32_t idx = lane; idx < ncand; idx += 32) {
+            Cand c = cand[idx];
+            const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
+            const double p = hypergeom_pvalue_exact(P.lf, P.N, s_c1[i], P.c2[j], c.k);
+            cand[idx].v = p;
+            Best b;
+            b.p = p;
+            b.k = c.k;
+            b.ij = c.ij;
+            if (better(b, best)) best = b;
+        }
+        if (better(zero, best)) best = zero;
+        // (5) warp-shuffle argmin with the reference tie-break
+        best = warp_best(best);
+        __syncwarp();
+        if (best.ij == 0xFFFFFFFFu || !(best.p < 1.0)) {
+            // no cell beats the cells the reference short-circuits to p = 1.0: needs the dense path
+            if (lane == 0) status[task] = 2;
+            __syncwarp();
+            continue;
+        }
+        const uint32_t bi = best.ij >> 16, bj = best.ij & 0xFFFFu;
+        const uint32_t bK = s_c1[bi], bn = P.c2[bj];
+        bool near = false;
+        if (best.p > 0.0) {
+            for (uint32_t idx = lane; idx < ncand; idx += 32) {
+                const Cand c = cand[idx];
+                if (c.ij == best.ij) continue;
+                const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
+                const bool same = (s_c1[i] == bK && P.c2[j] == bn && c.k == best.k);
+                if (!same && fabs(c.v - best.p) <= 1e-12 * best.p) near = true;
+            }
+        }
+        near = __any_sync(kFull, near);
+        if (lane == 0) {
+            dto_b200_record r;
+            r.rank1 = P.thr1[bi];
+            r.rank2 = P.thr2[bj];
+            r.set1_len = bK;
+            r.set2_len = bn;
+            r.intersection_size = best.k;
+            r.flags = record_flags | (near ? DTO_B200_FLAG_NEAR_TIE : 0u) | (WIDE ? DTO_B200_FLAG_PATH_WIDE : 0u);
+            r.population_size = P.N;
+            r.pvalue = best.p;
+            out[task] = r;
+            status[task] = 0;
+            atomicAdd(&counters[0], (unsigned long long)ncand);
+            atomicAdd(&counters[1], n_level2);
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// K3: dense grid
+// =====================================================================================================
+__global__ void full_hist_kernel(const Problem P, const uint16_t *__restrict__ pbrow, uint32_t *__restrict__ H) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n1_eff) return;
+    const uint32_t slot = pbrow[j];
+    const uint32_t b1 = P.bin1[j];
+    if (slot == kNoSlot || b1 == kNoSlot) return;
+    const uint32_t col = (slot / P.CHP) * P.CH + (slot % P.CHP);
+    atomicAdd(&H[(size_t)b1 * P.T2 + col], 1u);
+}
+
+__global__ void full_prefix_cols_kernel(int T1, int T2, uint32_t *__restrict__ H) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= T2) return;
+    uint32_t run = 0;
+    for (int i = 0; i < T1; ++i) {
+        run += H[(size_t)i * T2 + j];
+        H[(size_t)i * T2 + j] = run;
+    }
+}
+
+__global__ void full_prefix_rows_kernel(int T1, int T2, uint32_t *__restrict__ H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T1) return;
+    uint32_t run = 0;
+    for (int j = 0; j < T2; ++j) {
+        run += H[(size_t)i * T2 + j];
+        H[(size_t)i * T2 + j] = run;
+    }
+}
+
+__global__ void full_eval_kernel(const Problem P, const uint32_t *__restrict__ H, double *__restrict__ pv,
+                                 double *__restrict__ logp) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= P.T1 * P.T2) return;
+    const int i = cell / P.T2, j = cell % P.T2;
+    const uint64_t K = P.c1[i], n = P.c2[j], k = H[cell];
+    if (pv) pv[cell] = hypergeom_pvalue_exact(P.lf, P.N, K, n, k);
+    if (logp) logp[cell] = hypergeom_log_pvalue(P.lf, P.N, K, n, k);
+}
+
+__global__ void __launch_bounds__(1024) full_argmin_kernel(const Problem P, const uint32_t *__restrict__ H,
+                                                           const double *__restrict__ pv, uint32_t record_flags,
+                                                           dto_b200_record *__restrict__ out) {
+    __shared__ Best sb[32];
+    Best best;
+    best.p = CUDART_INF;
+    best.k = 0;
+    best.ij = 0xFFFFFFFFu;
+    const int cells = P.T1 * P.T2;
+    for (int cell = threadIdx.x; cell < cells; cell += blockDim.x) {
+        Best b;
+        b.p = pv[cell];
+        b.k = H[cell];
+        b.ij = ((uint32_t)(cell / P.T2) << 16) | (uint32_t)(cell % P.T2);
+        if (better(b, best)) best = b;
+    }
+    best = warp_best(best);
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Best b = sb[threadIdx.x];
+        if (threadIdx.x >= (blockDim.x >> 5)) b.ij = 0xFFFFFFFFu;
+        b = warp_best(b);
+        if (threadIdx.x == 0) {
+            const uint32_t bi = b.ij >> 16, bj = b.ij & 0xFFFFu;
+            dto_b200_record r;
+            r.rank1 = P.thr1[bi];
+            r.rank2 = P.thr2[bj];
+            r.set1_len = P.c1[bi];
+            r.set2_len = P.c2[bj];
+            r.intersection_size = b.k;
+            r.flags = record_flags | DTO_B200_FLAG_PATH_FULL;
+            r.population_size = P.N;
+            r.pvalue = b.p;
+            *out = r;
+        }
+    }
+}
+
+__global__ void pvalues_kernel(const double *__restrict__ lf, const uint64_t *__restrict__ N,
+                               const uint64_t *__restrict__ K, const uint64_t *__restrict__ n,
+                               const uint64_t *__restrict__ k, size_t count, double *__restrict__ out) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= count) return;
+    out[x] = hypergeom_pvalue_exact(lf, N[x], K[x], n[x], k[x]);
+}
+
+// =====================================================================================================
+// roofline probes
+// =====================================================================================================
+__global__ void fp64_probe_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 0.1, a2 = a0 + 0.2, a3 = a0 + 0.3;
+    double a4 = a0 + 0.4, a5 = a0 + 0.5, a6 = a0 + 0.6, a7 = a0 + 0.7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void hbm_copy_probe_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n) {
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x)
+        dst[x] = src[x];
+}
+
+// =====================================================================================================
+// launchers
+// =====================================================================================================
+template <int CH, bool WIDE>
+static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
+                                 uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
+                                 unsigned long long *counters, int grid, int warps, cudaStream_t st) {
+    using L = ScanLayout<CH, WIDE>;
+    const size_t smem = (((size_t)P.T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * L::per_warp;
+    auto kern = scan_kernel<CH, WIDE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, warps * 32, smem, st>>>(P, pb, task_ids, n_tasks, flags, out, status,
+                                          reinterpret_cast<Cand *>(wide_buf), counters);
+    return cudaGetLastError();
+}
+
+size_t scan_smem_bytes(int CH, bool wide, int T1, int warps) {
+    const size_t chp = (size_t)(CH | 1);
+    const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
+    const size_t q = (size_t)(32 * CH + 32) * 8;
+    const size_t per = d + q + 16 + (wide ? 0 : (size_t)kCandCap * sizeof(Cand));
+    return (((size_t)T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * per;
+}
+
+size_t cand_bytes() { return sizeof(Cand); }
+
+int pick_ch(int T2) {
+    static const int opts[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 48, 64};
+    const int need = (T2 + 31) / 32;
+    for (int o : opts)
+        if (o >= need) return o;
+    return -1;
+}
+
+template <bool WIDE>
+static cudaError_t launch_scan_w(const Problem &P, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
+                                 uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
+                                 unsigned long long *counters, int grid, int warps, cudaStream_t st) {
+#define DTO_CASE(X)                                                                                           \
+    case X:                                                                                                   \
+        return launch_scan_t<X, WIDE>(P, pb, task_ids, n_tasks, flags, out, status, wide_buf, counters, grid, \
+                                      warps, st);
+    switch (P.CH) {
+        DTO_CASE(1) DTO_CASE(2) DTO_CASE(4) DTO_CASE(8) DTO_CASE(12) DTO_CASE(16) DTO_CASE(20) DTO_CASE(24)
+        DTO_CASE(28) DTO_CASE(32) DTO_CASE(48) DTO_CASE(64)
+        default:
+            return cudaErrorInvalidValue;
+    }
+#undef DTO_CASE
+}
+
+cudaError_t launch_scan(const Problem &P, bool wide, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
+                        uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
+                        unsigned long long *counters, int grid, int warps, cudaStream_t st) {
+    return wide ? launch_scan_w<true>(P, pb, task_ids, n_tasks, flags, out, status, wide_buf, counters, grid, warps, st)
+                : launch_scan_w<false>(P, pb, task_ids, n_tasks, flags, out, status, wide_buf, counters, grid, warps, st);
+}
+
+cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, cudaStream_t st) {
+    const size_t bytes = (size_t)(P.levels + 1) * P.T1 * P.T2pad * sizeof(uint16_t);
+    cudaError_t e = cudaMemsetAsync(kcrit, 0xFF, bytes, st);
+    if (e != cudaSuccess) return e;
+    const int cells = P.T1 * P.T2;
+    build_kcrit_kernel<<<(cells + 255) / 256, 256, 0, st>>>(P, kcrit);
+    return cudaGetLastError();
+}
+
+size_t sigma_smem_bytes(const Problem &P, int B1, int B2) {
+    const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+    const int Bmax = B1 > B2 ? B1 : B2;
+    size_t b = (size_t)nmax * 4 + ((size_t)(1u << Bmax) * 2 + 1 + 32) * 4;
+    b += (size_t)P.pb_stride * 2;
+    const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
+    if (!identical) b += (size_t)P.n_common * 2 + 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+int pick_bucket_bits(uint32_t n) {
+    int lg = 0;
+    while ((1ull << lg) < n) ++lg;
+    int B = lg - 3;
+    if (B < 1) B = 1;
+    if (B > 13) B = 13;
+    return B;
+}
+
+cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
+                              uint32_t *pairing_out, int grid, cudaStream_t st) {
+    const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
+    const size_t smem = sigma_smem_bytes(P, B1, B2);
+    cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, int n_tasks,
+                           uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st) {
+    const int th = 256;
+    if (perm1) {  // validate perm1 is a permutation (scratch reused)
+        const size_t tot = (size_t)P.n1 * n_tasks;
+        invert_perm_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(perm1, P.n1, n_tasks, inv_scratch, err_flag);
+        check_perm_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(perm1, P.n1, n_tasks, inv_scratch, err_flag);
+    }
+    if (perm2) {
+        const size_t tot = (size_t)P.n2 * n_tasks;
+        invert_perm_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(perm2, P.n2, n_tasks, inv_scratch, err_flag);
+        check_perm_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(perm2, P.n2, n_tasks, inv_scratch, err_flag);
+    }
+    const size_t tot = (size_t)P.pb_stride * n_tasks;
+    compose_pairing_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(P, perm1, perm2 ? inv_scratch : nullptr,
+                                                                         n_tasks, pb);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_full_grid(const Problem &P, const uint16_t *pbrow, uint32_t *H, double *pv, double *logp,
+                             cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(H, 0, (size_t)P.T1 * P.T2 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    if (P.n1_eff) full_hist_kernel<<<(P.n1_eff + 255) / 256, 256, 0, st>>>(P, pbrow, H);
+    full_prefix_cols_kernel<<<(P.T2 + 127) / 128, 128, 0, st>>>(P.T1, P.T2, H);
+    full_prefix_rows_kernel<<<(P.T1 + 127) / 128, 128, 0, st>>>(P.T1, P.T2, H);
+    if (pv || logp) full_eval_kernel<<<(P.T1 * P.T2 + 127) / 128, 128, 0, st>>>(P, H, pv, logp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_full_argmin(const Problem &P, const uint32_t *H, const double *pv, uint32_t flags,
+                               dto_b200_record *out, cudaStream_t st) {
+    full_argmin_kernel<<<1, 1024, 0, st>>>(P, H, pv, flags, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pvalues(const double *lf, const uint64_t *N, const uint64_t *K, const uint64_t *n,
+                           const uint64_t *k, size_t count, double *out, cudaStream_t st) {
+    pvalues_kernel<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(lf, N, K, n, k, count, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_probe(double *out, int blocks, int threads, int iters, cudaStream_t st) {
+    fp64_probe_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hbm_probe(const void *src, void *dst, size_t bytes, int blocks, cudaStream_t st) {
+    hbm_copy_probe_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst),
+                                                  bytes / 16);
+    return cudaGetLastError();
+}
+
+}  // namespace dto

@@ -1,0 +1,51 @@
+"""Mirror of the reference's `run` module (src/run/*.rs)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+from .collections import RankedFeatureList
+from .dto import OptimizationResultRecord
+
+
+@dataclass
+class Task:
+    """src/run/task.rs:3-9"""
+
+    id: int
+    permute: bool
+
+
+def run_single_node_records(tasks: Sequence[Task], l1: RankedFeatureList, l2: RankedFeatureList, population_size: int,
+                            num_threads: int = 1, devices: Optional[Sequence[int]] = None, seed: int = 0) -> np.ndarray:
+    tp = np.array([1 if t.permute else 0 for t in tasks], dtype=np.uint8)
+    out = np.zeros(tp.size, dtype=capi.RECORD_DTYPE)
+    devs = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
+    capi.check(
+        capi.lib().dto_b200_run_single_node(
+            l1.handle, l2.handle, int(population_size), tp.ctypes.data_as(C.POINTER(C.c_uint8)), tp.size,
+            devs.ctypes.data_as(C.POINTER(C.c_int)) if devs.size else None, devs.size, int(seed),
+            out.ctypes.data_as(C.POINTER(capi.Record)),
+        )
+    )
+    return out
+
+
+def run_single_node(tasks: Sequence[Task], l1: RankedFeatureList, l2: RankedFeatureList, population_size: int,
+                    num_threads: int = 1, devices: Optional[Sequence[int]] = None, seed: int = 0) -> List[OptimizationResultRecord]:
+    """src/run/single_node.rs:83-137.  `num_threads` is accepted for signature compatibility; tasks are batched
+    onto the GPU(s) in `devices` (default: device 0).  Results come back in task order (the reference returns them
+    in thread-completion order; its only consumer partitions by `permuted`)."""
+    return [OptimizationResultRecord.from_np(r) for r in run_single_node_records(tasks, l1, l2, population_size, num_threads, devices, seed)]
+
+
+def run_multi_gpu(tasks, l1, l2, population_size, devices=None, seed: int = 0):
+    """Single-box replacement of run_multi_node (src/run/multi_node.rs:47-162): shard over all visible GPUs."""
+    from .engine import device_count
+
+    devs = list(devices) if devices is not None else list(range(device_count()))
+    return run_single_node(tasks, l1, l2, population_size, 1, devs, seed)

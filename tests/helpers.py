@@ -1,0 +1,122 @@
+"""Shared synthetic inputs and oracle/product glue for the tests.  Test infrastructure."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def ids_for(n, prefix="f"):
+    return [f"{prefix}{i + 1:06d}" for i in range(n)]
+
+
+def synthetic_pair(N, seed, sigma=0.25, tied_frac=0.0):
+    """list 1: rank(i) = i+1; list 2: rank of i + Normal(0, sigma*N) (sigma=None -> pure shuffle, 0 -> identical)."""
+    rng = np.random.default_rng(seed)
+    ids = ids_for(N)
+    r1 = np.arange(1, N + 1, dtype=np.uint32)
+    if sigma is None:
+        score = rng.permutation(N).astype(np.float64)
+    else:
+        score = np.arange(N) + rng.normal(0.0, sigma * N if sigma > 0 else 0.0, N)
+    order = np.argsort(score, kind="stable")
+    r2 = np.empty(N, dtype=np.uint32)
+    r2[order] = np.arange(1, N + 1, dtype=np.uint32)
+    if tied_frac > 0:
+        # collapse a fraction of features into tie groups with `min` ranking
+        for r in (r1, r2):
+            n_groups = max(1, int(N * tied_frac / 4))
+            starts = rng.choice(np.arange(1, N - 4), size=n_groups, replace=False)
+            for s in starts:
+                sel = (r >= s) & (r < s + 4)
+                r[sel] = s
+    return ids, r1, list(ids), r2
+
+
+def background_case(n_universe, n1, n2, seed):
+    """two lists over different subsets of a universe, ranks with gaps/ties, background = universe."""
+    rng = np.random.default_rng(seed)
+    uni = ids_for(n_universe, "g")
+    s1 = rng.choice(n_universe, size=n1, replace=False)
+    s2 = rng.choice(n_universe, size=n2, replace=False)
+    r1 = rng.integers(0, 3 * n1, size=n1).astype(np.uint32)  # rank 0 legal, gaps and ties
+    r2 = rng.integers(1, 2 * n2, size=n2).astype(np.uint32)
+    return [uni[i] for i in s1], r1, [uni[i] for i in s2], r2, uni
+
+
+def read_csv(path):
+    ids, ranks = [], []
+    with open(path) as f:
+        for line in f:
+            a, b = line.rstrip("\n").split(",")
+            ids.append(a.strip())
+            ranks.append(int(b))
+    return ids, np.array(ranks, dtype=np.uint32)
+
+
+def load_test_data():
+    ids1, r1 = read_csv(os.path.join(GOLDEN, "test_data", "ranklist1.csv"))
+    ids2, r2 = read_csv(os.path.join(GOLDEN, "test_data", "ranklist2.csv"))
+    bg = [ln.strip() for ln in open(os.path.join(GOLDEN, "test_data", "background.txt"))]
+    return ids1, r1, ids2, r2, bg
+
+
+def ten_gene_case():
+    """dto/optimize_main.rs:128-157"""
+    g1 = [f"gene{i}" for i in range(1, 11)]
+    g2 = ["gene7", "gene3", "gene9", "gene1", "gene5", "gene10", "gene4", "gene8", "gene6", "gene2"]
+    r = np.arange(1, 11, dtype=np.uint32)
+    return g1, r, g2, r.copy()
+
+
+def oracle_lists(ids1, r1, ids2, r2):
+    return O.OracleRankedList.make(ids1, r1), O.OracleRankedList.make(ids2, r2)
+
+
+def perms(n, P, seed):
+    rng = np.random.default_rng(seed)
+    return np.stack([rng.permutation(n).astype(np.uint32) for _ in range(P)])
+
+
+def perms_from_pairing(pairing, slot2_of_1, n2):
+    """Builds (perm1, perm2) index vectors (permuted.rs semantics) that realise a device pairing
+    pos2_of_pos1[j] (0xFFFFFFFF = position j holds a gene absent from list 2)."""
+    n1 = pairing.size
+    slot2_of_1 = np.asarray(slot2_of_1)
+    common1 = [a for a in range(n1) if slot2_of_1[a] >= 0]
+    other1 = [a for a in range(n1) if slot2_of_1[a] < 0]
+    paired_pos = [j for j in range(n1) if pairing[j] != 0xFFFFFFFF]
+    assert len(paired_pos) == len(common1)
+    perm1 = np.empty(n1, dtype=np.uint32)
+    perm2 = np.full(n2, 0xFFFFFFFF, dtype=np.uint32)
+    for t, j in enumerate(paired_pos):
+        a = common1[t]
+        perm1[j] = a
+        perm2[pairing[j]] = slot2_of_1[a]
+    unp = [j for j in range(n1) if pairing[j] == 0xFFFFFFFF]
+    for j, a in zip(unp, other1):
+        perm1[j] = a
+    used2 = set(int(x) for x in perm2 if x != 0xFFFFFFFF)
+    rest2 = [b for b in range(n2) if b not in used2]
+    free2 = [j for j in range(n2) if perm2[j] == 0xFFFFFFFF]
+    for j, b in zip(free2, rest2):
+        perm2[j] = b
+    return perm1, perm2
+
+
+def assert_record_matches(rec, ob, rel=1e-12):
+    """integer fields bit-exact; p within `rel` relative (exact when 0)."""
+    for f in ("rank1", "rank2", "set1_len", "set2_len", "intersection_size", "population_size"):
+        assert int(rec[f]) == int(ob[f]), (f, rec, ob)
+    p, q = float(rec["pvalue"]), float(ob["pvalue"])
+    if q == 0.0:
+        assert p == 0.0, (p, q)
+    else:
+        assert abs(p - q) <= rel * abs(q), (p, q)

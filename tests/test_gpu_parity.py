@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): overlap counts and optimal threshold pairs bit-exact; p-values within 1e-9
+relative in log p (here they agree to ~1e-13: the device sums the same ln_factorial table in statrs' order and
+differs only in exp()'s last ulp)."""
+import numpy as np
+import pytest
+
+import dual_threshold_optimization_b200 as dto
+from tests import helpers as H
+from tests.helpers import O
+
+pytestmark = pytest.mark.gpu
+
+LOGP_RTOL = 1e-9  # north_star tolerance, relative in log p
+
+
+def load(engine, ids1, r1, ids2, r2, background=None):
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    bg = dto.FeatureList(background) if background is not None else None
+    N = dto.compute_population_size(l1, l2, bg)
+    engine.load_lists(l1, l2, N)
+    o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+    assert O.compute_population_size(o1, o2, background) == N
+    assert np.array_equal(l1.thresholds(), o1.thresholds) and np.array_equal(l2.thresholds(), o2.thresholds)
+    return o1, o2, N, O.slot_map(o1, o2)
+
+
+def check_grid(engine, o1, o2, N, slot, perm1=None, perm2=None):
+    ov, pv, lp = engine.grid_debug(perm1, perm2, want_p=True, want_logp=True)
+    ref = O.grid_int(o1, o2, N, slot, perm1, perm2, want_logp=True)
+    assert np.array_equal(ov, ref.overlap), "overlap counts must be bit-exact"
+    zero = ref.p == 0.0
+    assert np.array_equal(pv == 0.0, zero), "underflow-to-zero cells must coincide"
+    nz = ~zero
+    assert np.allclose(pv[nz], ref.p[nz], rtol=1e-12, atol=0.0)
+    fin = np.isfinite(ref.logp)
+    assert np.array_equal(np.isfinite(lp), fin)
+    tol = LOGP_RTOL * np.maximum(np.abs(ref.logp[fin]), 1e-300) + 1e-13
+    assert np.all(np.abs(lp[fin] - ref.logp[fin]) <= tol), "log p outside the 1e-9 relative tolerance"
+    return ref
+
+
+CASES = {
+    "test_data": lambda: H.load_test_data(),
+    "ten_gene": lambda: H.ten_gene_case() + (None,),
+    "synthetic_300_ties": lambda: H.synthetic_pair(300, 3, 0.25, tied_frac=0.2) + (None,),
+    "background_330_290": lambda: H.background_case(400, 330, 290, 5),
+    "maxrank_1000": lambda: H.synthetic_pair(1000, 9, 0.3) + (None,),
+    "null_2000": lambda: H.synthetic_pair(2000, 13, None) + (None,),
+    "identical_1500": lambda: H.synthetic_pair(1500, 1, 0.0) + (None,),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_grid_and_unpermuted_optimum(engine, name):
+    ids1, r1, ids2, r2, bg = CASES[name]()
+    o1, o2, N, slot = load(engine, ids1, r1, ids2, r2, bg)
+    ref = check_grid(engine, o1, o2, N, slot)
+    rec = engine.run_unpermuted()
+    H.assert_record_matches(rec, ref.best)
+    assert not (int(rec["flags"]) & dto._capi.FLAG_PERMUTED)
+    if len(ids1) <= 400:  # the reference-faithful (string/HashSet/uncached) oracle agrees too
+        fb = O.optimize_faithful(o1, o2, N)
+        H.assert_record_matches(rec, {k: fb[k] for k in fb.dtype.names})
+
+
+def test_reference_goldens_through_the_gpu(engine):
+    # dto/optimize_main.rs:168-170
+    ids1, r1, ids2, r2 = H.ten_gene_case()
+    load(engine, ids1, r1, ids2, r2)
+    rec = engine.run_unpermuted()
+    assert (int(rec["rank1"]), int(rec["rank2"])) == (3, 4)
+    assert float(rec["pvalue"]) == pytest.approx(0.33333333333333337, rel=1e-15)
+    # README.md:174-184
+    ids1, r1, ids2, r2, bg = H.load_test_data()
+    load(engine, ids1, r1, ids2, r2, bg)
+    rec = engine.run_unpermuted()
+    assert [int(rec[f]) for f in ("rank1", "rank2", "set1_len", "set2_len", "intersection_size", "population_size")] == [24, 13, 24, 13, 12, 30]
+    assert float(rec["pvalue"]) == pytest.approx(0.15632183908046102, rel=1e-14)
+    # stat_operations/hypergeometric_pvalue.rs:27-31 and :56-87
+    p = engine.hypergeometric_pvalues([1000, 6060, 3, 3, 3, 3, 3, 10], [50, 5808, 1, 1, 1, 2, 2, 1], [60, 154, 1, 2, 3, 1, 2, 1], [10, 153, 1, 1, 1, 1, 2, 0])
+    want = [0.00044068070222441115, 0.010413637619010246, 1 / 3, 2 / 3, 1.0, 2 / 3, 1 / 3, 1.0]
+    assert np.allclose(p, want, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("name,P", [("test_data", 64), ("ten_gene", 32), ("background_330_290", 48), ("synthetic_300_ties", 48), ("null_2000", 24), ("identical_1500", 8)])
+def test_permuted_host_indices_match_oracle(engine, name, P):
+    ids1, r1, ids2, r2, bg = CASES[name]()
+    o1, o2, N, slot = load(engine, ids1, r1, ids2, r2, bg)
+    p1, p2 = H.perms(len(ids1), P, 100), H.perms(len(ids2), P, 200)
+    recs = engine.run_permuted_indices(p1, p2)
+    near = 0
+    for t in range(P):
+        ob = O.grid_int(o1, o2, N, slot, p1[t], p2[t]).best
+        assert int(recs[t]["flags"]) & dto._capi.FLAG_PERMUTED
+        if int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            near += 1  # the pick between ulp-level near ties is decided by libm noise: compare the value only
+            assert float(recs[t]["pvalue"]) == pytest.approx(float(ob["pvalue"]), rel=1e-11)
+            continue
+        H.assert_record_matches(recs[t], ob)
+    assert near <= max(1, P // 8)
+    # a few full grids under permutation
+    for t in range(min(P, 3)):
+        check_grid(engine, o1, o2, N, slot, p1[t], p2[t])
+
+
+@pytest.mark.parametrize("N,P,sigma", [(6000, 6, 0.25), (6000, 6, None), (20000, 3, None)])
+def test_baseline_sizes_match_oracle(engine, N, P, sigma):
+    """configs C2 / C3 of BASELINE.json at full feature counts (few tasks: the oracle needs ~seconds per task)."""
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, N, sigma)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    assert (o1.thresholds.size, o2.thresholds.size) == ({6000: 469, 20000: 589}[N],) * 2
+    lf = O.ln_factorial_table(pop)
+    rec = engine.run_unpermuted()
+    H.assert_record_matches(rec, O.grid_int(o1, o2, pop, slot, lf=lf, want_overlap=False, want_p=False).best)
+    p1, p2 = H.perms(N, P, 1), H.perms(N, P, 2)
+    recs = engine.run_permuted_indices(p1, p2)
+    for t in range(P):
+        ob = O.grid_int(o1, o2, pop, slot, p1[t], p2[t], lf=lf, want_overlap=False, want_p=False).best
+        if int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            assert float(recs[t]["pvalue"]) == pytest.approx(float(ob["pvalue"]), rel=1e-11)
+        else:
+            H.assert_record_matches(recs[t], ob)
+    ov, _, _ = engine.grid_debug(p1[0], p2[0], want_p=False)
+    assert np.array_equal(ov, O.grid_int(o1, o2, pop, slot, p1[0], p2[0], lf=lf, want_p=False).overlap)
+
+
+@pytest.mark.parametrize("name", ["null_2000", "background_330_290", "test_data"])
+def test_device_philox_permutations_replay_through_oracle(engine, name):
+    ids1, r1, ids2, r2, bg = CASES[name]()
+    o1, o2, N, slot = load(engine, ids1, r1, ids2, r2, bg)
+    P = 40
+    recs = engine.run_permuted_philox(seed=42, first_perm_id=1000, P=P)
+    n_common = int((slot >= 0).sum())
+    for t in range(0, P, 3):
+        pairing = engine.philox_pairing(42, 1000 + t)
+        paired = pairing[pairing != 0xFFFFFFFF]
+        assert paired.size == n_common and np.unique(paired).size == paired.size and paired.max() < len(ids2)
+        p1, p2 = H.perms_from_pairing(pairing, slot, len(ids2))
+        ob = O.grid_int(o1, o2, N, slot, p1, p2).best
+        if int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            assert float(recs[t]["pvalue"]) == pytest.approx(float(ob["pvalue"]), rel=1e-11)
+        else:
+            H.assert_record_matches(recs[t], ob)
+    # results are a pure function of (seed, permutation id): independent of batching / sharding
+    a = engine.run_permuted_philox(42, 1000, 17)
+    b = engine.run_permuted_philox(42, 1017, P - 17)
+    assert np.array_equal(np.concatenate([a, b]), recs)
+    assert not np.array_equal(engine.run_permuted_philox(43, 1000, P)["pvalue"], recs["pvalue"])
+
+
+def test_device_pairing_is_uniform_small_n(engine):
+    """All 4! pairings of a 4-feature problem are equally likely (chi-square over 4800 permutation ids)."""
+    from scipy import stats
+
+    ids = ["a", "b", "c", "d"]
+    r = np.array([1, 2, 3, 4], dtype=np.uint32)
+    load(engine, ids, r, ids, r)
+    counts = {}
+    for t in range(4800):
+        key = tuple(int(x) for x in engine.philox_pairing(5, t))
+        counts[key] = counts.get(key, 0) + 1
+    assert len(counts) == 24
+    chi = sum((c - 200.0) ** 2 / 200.0 for c in counts.values())
+    assert stats.chi2.sf(chi, 23) > 1e-4
+
+
+def test_device_pairing_position_marginals(engine):
+    """n=512: every (position, partner) cell is hit uniformly: chi-square on the 512x512 -> 16x16 coarse table."""
+    from scipy import stats
+
+    n = 512
+    ids1, r1, ids2, r2 = H.synthetic_pair(n, 2, None)
+    load(engine, ids1, r1, ids2, r2)
+    T = 600
+    table = np.zeros((16, 16))
+    fixed = 0
+    for t in range(T):
+        pr = engine.philox_pairing(99, t).astype(np.int64)
+        assert np.array_equal(np.sort(pr), np.arange(n))
+        np.add.at(table, (np.arange(n) // 32, pr // 32), 1)
+        fixed += int((pr == np.arange(n)).sum())
+    exp = T * n / 256.0
+    chi = ((table - exp) ** 2 / exp).sum()
+    assert stats.chi2.sf(chi, 15 * 15) > 1e-4
+    assert abs(fixed / T - 1.0) < 0.25  # fixed points of a uniform permutation ~ Poisson(1)
+
+
+def test_null_distribution_ks_against_oracle_null(engine):
+    """north_star: on-device Philox permutations are checked distributionally (KS on the null of min p)
+    against the reference-semantics null (oracle with numpy permutations)."""
+    from scipy import stats
+
+    N = 1500
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, 21, 0.25)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    dev = engine.run_permuted_philox(seed=7, first_perm_id=0, P=4000, want_records=False, want_minp=True)
+    lf = O.ln_factorial_table(pop)
+    p1, p2 = H.perms(N, 300, 11), H.perms(N, 300, 12)
+    ref = np.array([O.grid_int(o1, o2, pop, slot, p1[t], p2[t], lf=lf, want_overlap=False, want_p=False).best["pvalue"] for t in range(300)])
+    ks = stats.ks_2samp(np.log(dev), np.log(ref))
+    assert ks.pvalue > 1e-3, ks
+    # and the same test between two device seeds is also unremarkable
+    dev2 = engine.run_permuted_philox(seed=8, first_perm_id=0, P=4000, want_records=False, want_minp=True)
+    assert stats.ks_2samp(dev, dev2).pvalue > 1e-3
+
+
+def test_underflow_plateau_tiebreak(engine):
+    """Strongly concordant lists: the reference's p underflows to exactly 0.0 in many cells and the winner is
+    decided by the integer tie-break (largest intersection, then smallest (rank1, rank2))."""
+    N = 3000
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, 4, 0.0)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    ref = O.grid_int(o1, o2, pop, slot)
+    assert (ref.p == 0.0).sum() > 100
+    rec = engine.run_unpermuted()
+    assert float(rec["pvalue"]) == 0.0
+    H.assert_record_matches(rec, ref.best)
+    # near-identical: 2% of list 2 perturbed
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, 4, 0.002)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    H.assert_record_matches(engine.run_unpermuted(), O.grid_int(o1, o2, pop, slot).best)
+
+
+def test_degenerate_and_error_paths(engine):
+    # no common genes: every cell short-circuits to p = 1.0 -> first threshold pair wins (dense path)
+    l1 = dto.RankedFeatureList.from_(["a", "b", "c"], [1, 2, 3])
+    l2 = dto.RankedFeatureList.from_(["x", "y", "z"], [1, 2, 3])
+    engine.load_lists(l1, l2, 6)
+    rec = engine.run_unpermuted()
+    assert (int(rec["rank1"]), int(rec["rank2"]), int(rec["intersection_size"]), float(rec["pvalue"])) == (1, 1, 0, 1.0)
+    o1, o2 = H.oracle_lists(["a", "b", "c"], [1, 2, 3], ["x", "y", "z"], [1, 2, 3])
+    H.assert_record_matches(rec, O.optimize_faithful(o1, o2, 6))
+    # optimize_main.rs doctest :20-52: different features, population 4, permuted -> a Best record
+    l1 = dto.RankedFeatureList.from_(["gene1", "gene2", "gene3"], [1, 2, 3])
+    l2 = dto.RankedFeatureList.from_(["gene2", "gene3", "gene4"], [1, 2, 3])
+    r = dto.optimize(l1, l2, True, 4, engine=engine)
+    assert r.permuted and r.population_size == 4
+    # Hypergeometric::new panics when a set is larger than the population
+    with pytest.raises(dto.DtoPanic):
+        engine.load_lists(l1, l2, 2)
+    # empty list -> no thresholds -> unwrap panic in the reference
+    with pytest.raises(dto.DtoPanic):
+        engine.load_lists(dto.RankedFeatureList.from_([], []), l2, 4)
+    # not a permutation
+    engine.load_lists(l1, l2, 4)
+    with pytest.raises(dto.DtoError):
+        engine.run_permuted_indices(np.array([[0, 0, 1]], np.uint32), np.array([[0, 1, 2]], np.uint32))
+    # duplicate ids are rejected (documented deviation)
+    with pytest.raises(dto.DtoError):
+        engine.load_lists(dto.RankedFeatureList.from_(["a", "a"], [1, 2]), l2, 4)
+
+
+def test_run_single_node_and_epilogue(engine):
+    ids1, r1, ids2, r2, bg = H.load_test_data()
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    N = dto.compute_population_size(l1, l2, dto.FeatureList(bg))
+    tasks = [dto.Task(0, False)] + [dto.Task(i, True) for i in range(1, 1001)]  # config C1: 1 000 permutations
+    res = dto.run_single_node(tasks, l1, l2, N, 4)
+    assert len(res) == 1001 and not res[0].permuted and all(r.permuted for r in res[1:])
+    out = dto.empirical_pvalue(res)
+    assert {k: out[k] for k in ("rank1", "rank2", "set1_len", "set2_len", "unpermuted_intersection_size", "population_size", "fdr")} == {
+        "rank1": 24, "rank2": 13, "set1_len": 24, "set2_len": 13, "unpermuted_intersection_size": 12, "population_size": 30, "fdr": 0.0}
+    assert out["unpermuted_pvalue"] == pytest.approx(0.15632183908046102, rel=1e-14)
+    # the empirical p of the oracle's own null (numpy permutations) agrees statistically
+    o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+    slot = O.slot_map(o1, o2)
+    p1, p2 = H.perms(30, 1000, 3), H.perms(30, 1000, 4)
+    ref_null = np.array([O.grid_int(o1, o2, N, slot, p1[t], p2[t], want_overlap=False, want_p=False).best["pvalue"] for t in range(1000)])
+    ref_emp = float((ref_null <= 0.15632183908046102).mean())
+    assert abs(out["empirical_pvalue"] - ref_emp) < 0.07
+
+
+def test_cli_end_to_end(built):
+    import json
+    import os
+    import subprocess
+
+    td = os.path.join(H.GOLDEN, "test_data")
+    cli = dto._capi.CLI_PATH
+    r = subprocess.run([cli, "-1", f"{td}/ranklist1.csv", "-2", f"{td}/ranklist2.csv", "-b", f"{td}/background.txt", "-p", "5", "-t", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout)
+    assert list(out) == sorted(out)  # serde_json without preserve_order prints keys alphabetically
+    assert out["rank1"] == 24 and out["rank2"] == 13 and out["unpermuted_intersection_size"] == 12 and out["fdr"] == 0.0
+    assert '"unpermuted_pvalue": 0.15632183908046102' in r.stdout and '"fdr": 0.0' in r.stdout
+    assert "Permutations: 5" in r.stderr and "threshold lists" in r.stderr and ": 900" in r.stderr
