@@ -86,6 +86,21 @@ __device__ __forceinline__ double ln_binomial_tab(const double *__restrict__ lf,
     return __dsub_rn(__dsub_rn(lf[a], lf[b]), lf[a - b]);
 }
 
+// exp() as the reference's libm rounds it.  For normal results CUDA's exp (<= 1 ulp) is used as is.  Results in
+// the SUBNORMAL range carry only a few bits, so "1 ulp" there is a large relative error and decides whether a
+// term (hence a whole p-value) is exactly 0.0 -- which in turn decides the tie-break on the underflow plateau
+// (optimize_main.rs:77-80 compares p with ==).  glibc rounds exp(x) ONCE onto the 2^-1074 grid (e_exp.c
+// specialcase); do the same: q = exp(x + 1074 ln 2) computed with a two-part ln 2, rounded to nearest-even.
+__device__ __forceinline__ double exp_like_libm(double x) {
+    if (x >= -708.0) return exp(x);
+    if (x < -746.0) return 0.0;
+    const double ln2_hi = 6.93147180369123816490e-01;  // 32 significant bits: 1074 * ln2_hi is exact
+    const double ln2_lo = 1.90821492927058770002e-10;
+    const double t = __dadd_rn(__dadd_rn(x, 1074.0 * ln2_hi), 1074.0 * ln2_lo);
+    const double q = exp(t);  // in [~0.27, 2^52.6)
+    return __longlong_as_double(__double2ll_rn(q));  // the subnormal r * 2^-1074 has bit pattern r
+}
+
 // hypergeometric_pvalue(N, K, n, k): k == 0 -> 1; sf(k-1): x < min -> 1, x >= max -> 0, else ascending
 // sum_{i=k}^{min(K,n)} exp(lnC(K,i) + lnC(N-K,n-i) - lnC(N,n)).  Early exit is bit-preserving: past the mode
 // terms fall monotonically and a term below 2^-55 of the accumulator cannot change it (nor can later ones).
@@ -107,7 +122,7 @@ __device__ inline double hypergeom_pvalue_exact(const double *__restrict__ lf, u
         const double a = __dsub_rn(__dsub_rn(lfK, lf[i]), lf[K - i]);
         const uint64_t ni = n - i;
         const double b = (ni > NK) ? -CUDART_INF : __dsub_rn(__dsub_rn(lfNK, lf[ni]), lf[NK - ni]);
-        const double term = exp(__dsub_rn(__dadd_rn(a, b), ln_denom));
+        const double term = exp_like_libm(__dsub_rn(__dadd_rn(a, b), ln_denom));
         acc = __dadd_rn(acc, term);
         if (i > mode + 1 && term <= acc * 0x1p-55) break;
     }
