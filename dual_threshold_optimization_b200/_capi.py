@@ -25,7 +25,6 @@ ERR_IO = -6
 
 FLAG_PERMUTED = 0x1
 FLAG_NEAR_TIE = 0x2
-FLAG_PATH_WIDE = 0x4
 FLAG_PATH_FULL = 0x8
 
 
@@ -71,14 +70,18 @@ assert RECORD_DTYPE.itemsize == C.sizeof(Record) == 40
 class Stats(C.Structure):
     _fields_ = [
         ("tasks_fast", C.c_uint64),
-        ("tasks_wide", C.c_uint64),
         ("tasks_full", C.c_uint64),
         ("candidates", C.c_uint64),
         ("level2_cells", C.c_uint64),
+        ("refined_cells", C.c_uint64),
         ("kernel_launches", C.c_uint64),
         ("last_scan_kernel_ms", C.c_double),
         ("last_sigma_kernel_ms", C.c_double),
         ("last_scan_launches", C.c_uint64),
+        ("last_run_ms", C.c_double),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+        ("lptab_entries", C.c_uint64),
     ]
 
 
@@ -124,6 +127,7 @@ SYMBOLS = {
     "dto_b200_hypergeometric_pvalues": (C.c_int, [_vp, _u64p, _u64p, _u64p, _u64p, C.c_size_t, _f64p]),
     "dto_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "dto_b200_reset_stats": (C.c_int, [_vp]),
+    "dto_b200_last_batch_task_stats": (C.c_int, [_vp, _u32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dto_b200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "dto_b200_probe_fp64_tflops": (C.c_int, [_vp, _f64p]),
     "dto_b200_probe_hbm_gbs": (C.c_int, [_vp, _f64p]),

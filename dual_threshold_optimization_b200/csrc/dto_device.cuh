@@ -19,12 +19,16 @@ namespace dto {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint16_t kNoSlot = 0xFFFFu;  // "no partner / partner beyond the last threshold"
-constexpr int kMaxLevels = 16;         // screen levels 1..kMaxLevels (tau_l = 4^-l); level 0 = "valid cell"
+constexpr int kMaxLevels = 32;         // screen levels 1..kMaxLevels: tau_1 = 0.95, tau_l = 0.5 * 2^-((l-2)/2); level 0 = "valid cell"
 
 // log-domain safety margin: covers rounding of log pmf (~1e-10 abs) and of the statrs sum (~1e-12 rel)
 constexpr double kEps = 1e-6;
 // exp(x) underflows to exactly 0.0 in binary64 for x < -745.1332191019412.  A cell whose LARGEST tail term
 // lies below kZeroLo has p == 0.0 in the reference; between kZeroLo and kZeroHi it is evaluated exactly.
+// the ratio-recurrence tail reproduces log p of the reference to ~1e-10 (both sum the same ln-factorial table, whose
+// 7-term log pmf carries ~1e-10 absolute rounding); cells within kRefineEps of the minimum go to the exact stage
+constexpr double kRefineEps = 1e-8;
+constexpr uint32_t kRefinedBit = 0x80000000u;
 constexpr double kZeroLo = -745.14;
 constexpr double kZeroHi = -745.12;
 
@@ -35,6 +39,7 @@ struct Problem {
     int CHP;         // CH | 1: padded stride of the per-warp row histogram (conflict-free LDS)
     int T2pad;       // 32 * CH
     int levels;      // number of screen levels beyond level 0
+    int debug_task;  // diagnostics: task index whose refined cells are printed (-1 = off)
     uint32_t n1, n2;
     uint32_t n1_eff;     // #list-1 positions whose rank is <= the last threshold of list 1
     uint32_t pb_stride;  // u16 elements per permutation row of the partner-bin array
@@ -47,6 +52,8 @@ struct Problem {
     const double *rowA;  // [T1] lf[K] + lf[N-K]
     const double *colB;  // [T2] lf[n] + lf[N-n] - lf[N]
     const uint16_t *kcrit;     // [(levels+1)][T1][T2pad], column j stored at (j % CH) * 32 + j / CH
+    const uint2 *cellmeta;     // [T1*T2] {offset into lptab, kbase | count << 16}: log p tabulated for k in [kbase, kbase+count)
+    const double *lptab;       // log p (ratio-recurrence tail, ~1e-10) for every (cell, k) between tau_1 and tau_levels
     const uint16_t *dslot2;    // [n2] row-histogram slot of list-2 position (or kNoSlot)
     const uint16_t *bin1;      // [n1] threshold bin of list-1 position (or kNoSlot)
     const uint16_t *bin2;      // [n2]

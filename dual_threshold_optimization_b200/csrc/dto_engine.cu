@@ -95,15 +95,18 @@ struct dto_b200_ctx {
     bool has_problem = false;
     Problem P{};
     // problem tables
-    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2;
+    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts;
     // batch state
-    DevBuf d_pb, d_records, d_status, d_counters, d_taskids, d_wide, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
-        d_err, d_pair, d_minp;
+    DevBuf d_pb, d_records, d_status, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
+        d_err, d_pair, d_minp, d_tstats;
+    bool opt_task_stats = false;
+    int opt_debug_task = -1;
+    int last_batch_n = 0;
     PinnedBuf h_records, h_status, h_stage;
     // options
     int opt_batch = 0;  // 0 = auto
     int opt_warps = 8;
-    int opt_levels = 12;
+    int opt_levels = 32;
     dto_b200_stats stats{};
 };
 
@@ -135,52 +138,39 @@ int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags) {
     CUDA_TRY(ctx->h_status.ensure((size_t)n * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status.p, 0xFF, (size_t)n * 4, ctx->stream));
     int warps = ctx->opt_warps;
-    while (warps > 1 && scan_smem_bytes(P.CH, false, P.T1, warps) > ctx->smem_optin / ((P.CH > 32) ? 1 : 2)) --warps;
-    if (scan_smem_bytes(P.CH, false, P.T1, warps) > ctx->smem_optin)
+    while (warps > 1 && scan_smem_bytes(P.CH, P.T1, warps) > ctx->smem_optin / ((P.CH > 32) ? 1 : 2)) --warps;
+    if (scan_smem_bytes(P.CH, P.T1, warps) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "scan kernel does not fit shared memory (T1=%d T2=%d)", P.T1, P.T2);
     const int ctas_needed = (n + warps - 1) / warps;
     const int grid = std::min(ctas_needed, ctx->sm_count * 2);
+    if (ctx->opt_task_stats) {
+        CUDA_TRY(ctx->d_tstats.ensure((size_t)n * 4 * kTaskStatWords));
+        CUDA_TRY(cudaMemsetAsync(ctx->d_tstats.p, 0, (size_t)n * 4 * kTaskStatWords, ctx->stream));
+    }
+    ctx->last_batch_n = n;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + 7, 0, 8, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CUDA_TRY(launch_scan(P, false, ctx->d_pb.as<uint16_t>(), nullptr, n, flags, ctx->d_records.as<dto_b200_record>(),
-                         ctx->d_status.as<uint32_t>(), nullptr, ctx->d_counters.as<unsigned long long>(), grid, warps,
-                         ctx->stream));
+    CUDA_TRY(launch_scan(P, ctx->d_pb.as<uint16_t>(), n, flags, ctx->d_records.as<dto_b200_record>(),
+                         ctx->d_status.as<uint32_t>(), ctx->d_counters.as<unsigned long long>(),
+                         ctx->opt_task_stats ? ctx->d_tstats.as<uint32_t>() : nullptr, grid, warps, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.kernel_launches += 1;
     ctx->stats.last_scan_launches += 1;
     CUDA_TRY(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += (uint64_t)n * 4;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->stats.last_scan_kernel_ms += ms;
 
     const uint32_t *st = ctx->h_status.as<uint32_t>();
-    std::vector<uint32_t> wide, full;
+    std::vector<uint32_t> full;
     for (int t = 0; t < n; ++t) {
         if (st[t] == 0) continue;
-        if (st[t] == 1) wide.push_back((uint32_t)t);
-        else if (st[t] == 2) full.push_back((uint32_t)t);
+        if (st[t] == 2) full.push_back((uint32_t)t);
         else return fail(DTO_B200_ERR_CUDA, "scan kernel left task %d unprocessed (status %u)", t, st[t]);
     }
-    ctx->stats.tasks_fast += (uint64_t)(n - (int)wide.size() - (int)full.size());
-    if (!wide.empty()) {
-        const int wwarps = 4, wgrid_max = 8;
-        const size_t slot_bytes = (size_t)P.T1 * P.T2 * cand_bytes();
-        const int wgrid = std::min(wgrid_max, (int)((wide.size() + wwarps - 1) / wwarps));
-        CUDA_TRY(ctx->d_wide.ensure(slot_bytes * wwarps * wgrid));
-        CUDA_TRY(ctx->d_taskids.ensure(wide.size() * 4));
-        CUDA_TRY(cudaMemcpyAsync(ctx->d_taskids.p, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(launch_scan(P, true, ctx->d_pb.as<uint16_t>(), ctx->d_taskids.as<uint32_t>(), (int)wide.size(), flags,
-                             ctx->d_records.as<dto_b200_record>(), ctx->d_status.as<uint32_t>(), ctx->d_wide.p,
-                             ctx->d_counters.as<unsigned long long>(), wgrid, wwarps, ctx->stream));
-        ctx->stats.kernel_launches += 1;
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        for (uint32_t t : wide) {
-            if (st[t] == 2) full.push_back(t);
-            else if (st[t] != 0) return fail(DTO_B200_ERR_CUDA, "wide scan failed on task %u (status %u)", t, st[t]);
-            else ctx->stats.tasks_wide += 1;
-        }
-    }
+    ctx->stats.tasks_fast += (uint64_t)(n - (int)full.size());
     if (!full.empty()) {
         const size_t cells = (size_t)P.T1 * P.T2;
         CUDA_TRY(ctx->d_H.ensure(cells * 4));
@@ -206,10 +196,11 @@ int need_problem(dto_b200_ctx *ctx) {
 }
 
 int pull_counters(dto_b200_ctx *ctx) {
-    unsigned long long c[4];
+    unsigned long long c[8];
     CUDA_TRY(cudaMemcpy(c, ctx->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost));
     ctx->stats.candidates = c[0];
     ctx->stats.level2_cells = c[1];
+    ctx->stats.refined_cells = c[2];
     return DTO_B200_OK;
 }
 
@@ -270,10 +261,10 @@ void dto_b200_destroy(dto_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_c1, &ctx->d_c2, &ctx->d_thr1, &ctx->d_thr2, &ctx->d_lf, &ctx->d_rowA, &ctx->d_colB,
-                      &ctx->d_kcrit, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
-                      &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_taskids, &ctx->d_wide, &ctx->d_H,
+                      &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
+                      &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_H,
                       &ctx->d_pv, &ctx->d_logp, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_err, &ctx->d_pair,
-                      &ctx->d_minp};
+                      &ctx->d_minp, &ctx->d_tstats};
     for (DevBuf *b : bufs) b->release();
     ctx->h_records.release();
     ctx->h_status.release();
@@ -293,6 +284,11 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
     } else if (s == "warps_per_cta") {
         if (value < 1 || value > kScanThreads / 32) return fail(DTO_B200_ERR_INVALID, "warps_per_cta must be 1..8");
         ctx->opt_warps = (int)value;
+    } else if (s == "debug_task") {
+        ctx->opt_debug_task = (int)value;
+        ctx->P.debug_task = (int)value;
+    } else if (s == "task_stats") {
+        ctx->opt_task_stats = value != 0;
     } else if (s == "levels") {
         if (value < 0 || value > kMaxLevels) return fail(DTO_B200_ERR_INVALID, "levels must be 0..%d", kMaxLevels);
         if (ctx->has_problem) return fail(DTO_B200_ERR_STATE, "set 'levels' before dto_b200_set_problem");
@@ -310,6 +306,17 @@ int dto_b200_get_stats(dto_b200_ctx *ctx, dto_b200_stats *out) {
     rc = pull_counters(ctx);
     if (rc) return rc;
     *out = ctx->stats;
+    return DTO_B200_OK;
+}
+
+int dto_b200_last_batch_task_stats(dto_b200_ctx *ctx, uint32_t *out, size_t max_tasks, size_t *n_out) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!out || !n_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    if (!ctx->opt_task_stats) return fail(DTO_B200_ERR_STATE, "set option 'task_stats' to 1 first");
+    const size_t n = std::min(max_tasks, (size_t)ctx->last_batch_n);
+    CUDA_TRY(cudaMemcpy(out, ctx->d_tstats.p, n * 4 * kTaskStatWords, cudaMemcpyDeviceToHost));
+    *n_out = n;
     return DTO_B200_OK;
 }
 
@@ -366,6 +373,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.CHP = P.CH | 1;
     P.T2pad = 32 * P.CH;
     P.levels = ctx->opt_levels;
+    P.debug_task = ctx->opt_debug_task;
     P.n1 = (uint32_t)n1;
     P.n2 = (uint32_t)n2;
     P.N = population;
@@ -379,7 +387,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
                     "(%llu)",
                     c1[T1 - 1], c2[T2 - 1], (unsigned long long)population);
     P.n1_eff = c1[T1 - 1];
-    P.pb_stride = ((P.n1_eff + 64 + 63) / 64) * 64;
+    P.pb_stride = ((P.n1_eff + 1 + 255) / 256) * 256;  // whole 256-position chunks (cp.async staging in the scan)
     std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(n2 ? n2 : 1);
     for (size_t j = 0; j < n1; ++j) {
         const size_t b = std::lower_bound(thr1, thr1 + T1, ranks1[j]) - thr1;
@@ -396,11 +404,15 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     for (size_t i = 0; i < T1; ++i) rowA[i] = lf[c1[i]] + lf[population - c1[i]];
     for (size_t j = 0; j < T2; ++j) colB[j] = lf[c2[j]] + lf[population - c2[j]] - lf[population];
     P.level_log[0] = INFINITY;
-    for (int l = 1; l <= kMaxLevels; ++l) P.level_log[l] = -(double)l * std::log(4.0);
+    // tau_1 = 0.95 ends the unscreened phase at once; then half-octave steps 0.5, 0.354, 0.25, ... so that a permutation
+    // whose running minimum sits just above a level still screens out everything more than ~1.4x above it
+    P.level_log[1] = std::log(0.95);
+    for (int l = 2; l <= kMaxLevels; ++l) P.level_log[l] = std::log(0.5) - 0.5 * (double)(l - 2) * std::log(2.0);
 
     auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = b.ensure(bytes);
         if (e != cudaSuccess) return e;
+        ctx->stats.h2d_bytes += bytes;
         return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
     CUDA_TRY(up(ctx->d_c1, c1.data(), T1 * 4));
@@ -427,8 +439,30 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.bin1 = ctx->d_bin1.as<uint16_t>();
     P.bin2 = ctx->d_bin2.as<uint16_t>();
     P.slot2_of_1 = ctx->d_slot2.as<int32_t>();
-    CUDA_TRY(launch_build_kcrit(P, ctx->d_kcrit.as<uint16_t>(), ctx->stream));
-    ctx->stats.kernel_launches += 1;
+    // screen tables, then the log-p table: counts -> exclusive scan (host; a few hundred thousand words) -> fill
+    const size_t cells = T1 * T2;
+    CUDA_TRY(ctx->d_counts.ensure(cells * 4));
+    CUDA_TRY(ctx->d_meta.ensure(cells * 8));
+    CUDA_TRY(launch_build_kcrit(P, ctx->d_kcrit.as<uint16_t>(), ctx->d_counts.as<uint32_t>(), ctx->d_meta.as<uint2>(), ctx->stream));
+    std::vector<uint32_t> counts(cells);
+    CUDA_TRY(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    uint64_t total = 0;
+    for (size_t c = 0; c < cells; ++c) {
+        const uint32_t v = counts[c];
+        counts[c] = (uint32_t)total;
+        total += v;
+    }
+    if (total > 0xFFFFFFFFull) return fail(DTO_B200_ERR_UNSUPPORTED, "log-p table too large (%llu entries)", (unsigned long long)total);
+    CUDA_TRY(ctx->d_lptab.ensure((size_t)(total ? total : 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_counts.p, counts.data(), cells * 4, cudaMemcpyHostToDevice, ctx->stream));
+    P.cellmeta = ctx->d_meta.as<uint2>();
+    P.lptab = ctx->d_lptab.as<double>();
+    CUDA_TRY(launch_fill_lptab(P, ctx->d_counts.as<uint32_t>(), ctx->d_meta.as<uint2>(), ctx->d_lptab.as<double>(), ctx->stream));
+    ctx->stats.kernel_launches += 3;
+    ctx->stats.h2d_bytes += cells * 4;
+    ctx->stats.d2h_bytes += cells * 4;
+    ctx->stats.lptab_entries = total;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     ctx->P = P;
     ctx->has_problem = true;
@@ -449,6 +483,7 @@ int dto_b200_run_unpermuted(dto_b200_ctx *ctx, dto_b200_record *record_out) {
     rc = run_tasks(ctx, 1, 0u);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(record_out, ctx->d_records.p, sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += sizeof(dto_b200_record);
     return DTO_B200_OK;
 }
 
@@ -474,6 +509,7 @@ int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, cons
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_perm1.p, perm1 + done * P.n1, (size_t)n * P.n1 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_perm2.p, perm2 + done * P.n2, (size_t)n * P.n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += (uint64_t)n * ((uint64_t)P.n1 + P.n2) * 4;
         CUDA_TRY(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
         CUDA_TRY(launch_compose(P, ctx->d_perm1.as<uint32_t>(), ctx->d_perm2.as<uint32_t>(), n, ctx->d_inv.as<uint32_t>(),
                                 ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
@@ -485,6 +521,7 @@ int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, cons
         rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpy(records_out + done, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += (uint64_t)n * sizeof(dto_b200_record) + 4;
     }
     return DTO_B200_OK;
 }
@@ -505,6 +542,17 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
     ctx->stats.last_sigma_kernel_ms = 0;
     ctx->stats.last_scan_launches = 0;
     if (h_records || h_minp) CUDA_TRY(ctx->h_records.ensure(std::min(batch, Pn) * sizeof(dto_b200_record)));
+    cudaEvent_t run_begin = nullptr, run_end = nullptr;
+    CUDA_TRY(cudaEventCreate(&run_begin));
+    CUDA_TRY(cudaEventCreate(&run_end));
+    CUDA_TRY(cudaEventRecord(run_begin, ctx->stream));
+    struct EvGuard {
+        cudaEvent_t a, b;
+        ~EvGuard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } guard{run_begin, run_end};
     for (size_t done = 0; done < Pn; done += batch) {
         const int n = (int)std::min(batch, Pn - done);
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
@@ -521,6 +569,7 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
         if (h_records || h_minp) {
             dto_b200_record *stage = ctx->h_records.as<dto_b200_record>();
             CUDA_TRY(cudaMemcpyAsync(stage, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->stats.d2h_bytes += (uint64_t)n * sizeof(dto_b200_record);
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             if (h_records) memcpy(h_records + done, stage, (size_t)n * sizeof(dto_b200_record));
             if (h_minp)
@@ -534,6 +583,11 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
                                        sizeof(dto_b200_record), sizeof(double), (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
         if (d_records_out || d_minp_out) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
+    CUDA_TRY(cudaEventRecord(run_end, ctx->stream));
+    CUDA_TRY(cudaEventSynchronize(run_end));
+    float run_ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&run_ms, run_begin, run_end));
+    ctx->stats.last_run_ms = run_ms;
     return DTO_B200_OK;
 }
 

@@ -13,12 +13,19 @@
 //                              also the last-resort path for degenerate tasks (min p >= 1)
 #include "dto_kernels.cuh"
 
+#include <cstdio>
+
 namespace dto {
 
 // =====================================================================================================
 // K2: critical-overlap tables
 // =====================================================================================================
-__global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint16_t *__restrict__ kcrit) {
+// pass 0: write the kcrit tables and, per cell, kbase = kcrit_1 and count = #k tabulated (k from kcrit_1 up to, not
+//         including, kcrit_levels: the range where the screen can pass a cell at a tabulated level)
+// pass 1: fill lptab[offset + (k - kbase)] = log p(k) for that range (offsets = exclusive scan of the counts)
+__global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint16_t *__restrict__ kcrit, int pass,
+                                                          uint32_t *__restrict__ counts, uint2 *__restrict__ meta,
+                                                          double *__restrict__ lptab) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= P.T1 * P.T2) return;
     const int i = cell / P.T2, j = cell % P.T2;
@@ -26,11 +33,22 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
     const uint64_t K = P.c1[i], n = P.c2[j];
     const uint64_t lower = (K + n > N) ? (K + n - N) : 0;
     const uint64_t upper = K < n ? K : n;
-    if (lower + 1 > upper) return;  // no valid k: table stays 0xFFFF
+    if (lower + 1 > upper) {  // no valid k: table stays 0xFFFF
+        if (pass == 0) counts[cell] = 0;
+        return;
+    }
+    uint32_t tab_lo = 0, tab_n = 0;  // mode 1: tabulated range
+    if (pass == 1) {
+        const uint2 m = meta[cell];
+        tab_lo = m.y & 0xFFFFu;
+        tab_n = m.y >> 16;
+        if (tab_n == 0) return;
+    }
+    uint32_t kc1 = 0xFFFFu, kcL = 0xFFFFu;  // mode 0: kcrit at level 1 and at the deepest level
     const size_t col = (size_t)(j % P.CH) * 32 + (size_t)(j / P.CH);
     const size_t level_stride = (size_t)P.T1 * P.T2pad;
     uint16_t *dst = kcrit + (size_t)i * P.T2pad + col;
-    dst[0] = (uint16_t)(lower + 1);  // level 0: every cell the reference does not short-circuit to p = 1
+    if (pass == 0) dst[0] = (uint16_t)(lower + 1);  // level 0: every cell the reference does not short-circuit to p = 1
 
     const double rowA = P.rowA[i], colB = P.colB[j];
     auto lpmf = [&](uint64_t x) { return log_pmf(P, rowA, colB, (uint32_t)K, (uint32_t)n, (uint32_t)x); };
@@ -39,7 +57,11 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
     if (xs > upper) xs = upper;
     int l = P.levels;
     if (lpmf(xs) < -80.0) {  // the whole valid range is negligible (support starts far above the mode)
-        for (; l >= 1; --l) dst[l * level_stride] = (uint16_t)(lower + 1);
+        if (pass == 0) {
+            for (; l >= 1; --l) dst[l * level_stride] = (uint16_t)(lower + 1);
+            counts[cell] = 0;
+            meta[cell] = make_uint2(0u, (uint32_t)(lower + 1));
+        }
         return;
     }
     uint64_t x_end = upper;
@@ -57,19 +79,47 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
     double S = 0.0;
     for (;;) {
         S += t;  // p(k) up to a tail below e^-80
-        while (l >= 1 && S > exp(P.level_log[l]) * (1.0 + 1e-6)) {
-            dst[l * level_stride] = (k + 1 <= upper) ? (uint16_t)(k + 1) : kNoSlot;
-            --l;
-        }
-        if (l == 0) break;
-        if (k == lower + 1) {
-            for (; l >= 1; --l) dst[l * level_stride] = (uint16_t)(lower + 1);
-            break;
+        if (pass == 1) {
+            if (k >= tab_lo && k < tab_lo + tab_n) lptab[meta[cell].x + (uint32_t)(k - tab_lo)] = log(S);
+            if (k <= tab_lo) break;
+        } else {
+            while (l >= 1 && S > exp(P.level_log[l]) * (1.0 + 1e-6)) {
+                const uint16_t v = (k + 1 <= upper) ? (uint16_t)(k + 1) : kNoSlot;
+                dst[l * level_stride] = v;
+                if (l == P.levels) kcL = v;
+                if (l == 1) kc1 = v;
+                --l;
+            }
+            if (l == 0) break;
+            if (k == lower + 1) {
+                for (; l >= 1; --l) {
+                    dst[l * level_stride] = (uint16_t)(lower + 1);
+                    if (l == P.levels) kcL = (uint16_t)(lower + 1);
+                    if (l == 1) kc1 = (uint16_t)(lower + 1);
+                }
+                break;
+            }
         }
         // pmf(k-1) = pmf(k) * k (N-K-n+k) / ((K-k+1)(n-k+1))
         t *= ((double)k * (double)(N - K - n + k)) / ((double)(K - k + 1) * (double)(n - k + 1));
         --k;
     }
+    if (pass == 0) {
+        // tabulate k in [kc1, min(kcL, upper + 1)): cells the screen can pass at levels 1 .. levels-1; deeper (k >= kcL)
+        // or shallower (k < kc1, only reachable at level 0) cells take the closed-form / recurrence path in the scan
+        uint32_t cnt = 0;
+        if (P.levels >= 2 && kc1 != 0xFFFFu) {
+            const uint32_t hi = (kcL == 0xFFFFu) ? (uint32_t)upper + 1u : (uint32_t)kcL;
+            cnt = hi > kc1 ? hi - kc1 : 0u;
+        }
+        counts[cell] = cnt;
+        meta[cell] = make_uint2(0u, (uint32_t)kc1 | (cnt << 16));
+    }
+}
+
+__global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ offsets, uint2 *__restrict__ meta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < cells) meta[c].x = offsets[c];
 }
 
 // =====================================================================================================
@@ -301,17 +351,18 @@ __global__ void compose_pairing_kernel(const Problem P, const uint32_t *__restri
 struct __align__(16) Cand {
     uint32_t ij;
     uint32_t k;
-    double v;  // log lower bound of p while screening, then the exact p
+    double v;  // log lower bound of p
 };
 
-template <int CH, bool WIDE>
+template <int CH>
 struct ScanLayout {
     static constexpr int CHP = CH | 1;
     static constexpr int QCAP = 32 * CH + 32;
-    static constexpr int CAP = WIDE ? 0 : kCandCap;
+    static constexpr int CAP = kCandCap;
     static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
     static constexpr size_t q_bytes = (size_t)QCAP * 8;
-    static constexpr size_t per_warp = d_bytes + q_bytes + 16 + (size_t)CAP * sizeof(Cand);
+    static constexpr size_t ring_bytes = (size_t)kRing * 2;  // partner-slot staging ring (cp.async), 4 chunks of 256
+    static constexpr size_t per_warp = d_bytes + q_bytes + 16 + (size_t)CAP * sizeof(Cand) + ring_bytes;
 };
 
 __device__ __forceinline__ uint32_t compact_cands(Cand *c, uint32_t n, double theta, int lane) {
@@ -334,16 +385,41 @@ __device__ __forceinline__ uint32_t compact_cands(Cand *c, uint32_t n, double th
     return out;
 }
 
-template <int CH, bool WIDE>
-__global__ void __launch_bounds__(kScanThreads, (WIDE || CH > 32) ? 1 : 2)
-scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__restrict__ task_ids, int n_tasks,
-            uint32_t record_flags, dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
-            Cand *__restrict__ wide_buf, unsigned long long *__restrict__ counters) {
-    using L = ScanLayout<CH, WIDE>;
+// Running exact optimum of one lane / one warp, with the "near tie" witness: some OTHER (K, n, k) whose p lies
+// within 1e-12 relative of the optimum (the reference's pick between such cells hangs on the last ulp of its exp()).
+struct Exact {
+    Best best;
+    bool near;
+};
+
+__device__ __forceinline__ bool close_not_same(const Problem &P, const uint32_t *s_c1, const Best &a, const Best &b) {
+    if (a.ij == 0xFFFFFFFFu || b.ij == 0xFFFFFFFFu) return false;
+    if (a.p == 0.0 && b.p == 0.0) return false;  // exact ties at 0.0 are settled by the integer tie-break
+    if (fabs(a.p - b.p) > 1e-12 * fmax(a.p, b.p)) return false;
+    const bool same = (a.k == b.k) && (s_c1[a.ij >> 16] == s_c1[b.ij >> 16]) && (P.c2[a.ij & 0xFFFFu] == P.c2[b.ij & 0xFFFFu]);
+    return !same;
+}
+
+__device__ __forceinline__ void merge_exact(const Problem &P, const uint32_t *s_c1, Exact &acc, const Best &b, bool b_near) {
+    const bool close = close_not_same(P, s_c1, acc.best, b);
+    if (better(b, acc.best)) {
+        acc.near = b_near || close;
+        acc.best = b;
+    } else {
+        acc.near = acc.near || close;
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : 2)
+scan_kernel(const Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
+            dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
+            unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats) {
+    using L = ScanLayout<CH>;
     constexpr int CHP = L::CHP;
+    constexpr uint32_t cap = (uint32_t)L::CAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
     uint32_t *s_c1 = reinterpret_cast<uint32_t *>(smem_raw);  // [T1] shared by the CTA
     const size_t c1_bytes = ((size_t)P.T1 * 4 + 15) & ~(size_t)15;
     unsigned char *wbase = smem_raw + c1_bytes + (size_t)warp * L::per_warp;
@@ -351,17 +427,22 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__
     uint32_t *Qij = reinterpret_cast<uint32_t *>(wbase + L::d_bytes);
     uint32_t *Qk = Qij + L::QCAP;
     uint32_t *qcnt = Qk + L::QCAP;
-    Cand *cand = WIDE ? wide_buf + (size_t)(blockIdx.x * warps_per_cta + warp) * (size_t)P.T1 * P.T2
-                      : reinterpret_cast<Cand *>(wbase + L::d_bytes + L::q_bytes + 16);
-    const uint32_t cap = WIDE ? (uint32_t)(P.T1 * P.T2) : (uint32_t)L::CAP;
+    Cand *cand = reinterpret_cast<Cand *>(wbase + L::d_bytes + L::q_bytes + 16);
+    uint16_t *ring = reinterpret_cast<uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
     const unsigned lt = (1u << lane) - 1u;
 
     for (int x = threadIdx.x; x < P.T1; x += blockDim.x) s_c1[x] = P.c1[x];
     __syncthreads();
 
-    for (int t = blockIdx.x * warps_per_cta + warp; t < n_tasks; t += gridDim.x * warps_per_cta) {
-        const uint32_t task = task_ids ? task_ids[t] : (uint32_t)t;
+    // dynamic scheduling: permutations differ in cost (the occasional one has a wide blob of near-minimal cells)
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(reinterpret_cast<unsigned int *>(&counters[7]), 1u);
+        task = __shfl_sync(kFull, task, 0);
+        if (task >= n_tasks) break;
         const uint16_t *__restrict__ row = pb + (size_t)task * P.pb_stride;
+        const long long t_begin = clock64();
         for (int x = lane; x < 32 * CHP; x += 32) D[x] = 0;
         if (lane == 0) *qcnt = 0;
         __syncwarp();
@@ -373,15 +454,83 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__
         double theta = CUDART_INF;  // certified: log(min p of the reference) <= theta
         int level = 0;
         uint32_t ncand = 0;
-        bool overflow = false;
+        Exact ex;  // per-lane running optimum over everything evaluated exactly so far
+        ex.best.p = CUDART_INF;
+        ex.best.k = 0;
+        ex.best.ij = 0xFFFFFFFFu;
+        ex.near = false;
         Best zero;  // best cell on the underflow plateau (reference p == 0.0)
         zero.p = 0.0;
         zero.k = 0;
         zero.ij = 0xFFFFFFFFu;
-        unsigned long long n_level2 = 0;
+        unsigned long long n_level2 = 0, n_eval = 0, n_refine = 0;
+        long long tm_drain = 0, tm_refine = 0, tm_eval = 0, tm_scatter = 0, tm_compact = 0, n_drain_iter = 0;
+        const bool timing = task_stats != nullptr;
+
+        // (3b) refine: tail by the ratio recurrence (no exp, no table walk) -> log p to ~1e-10 for every buffered
+        //      candidate not refined yet; tightens theta so that only cells within 1e-8 of the minimum survive
+        auto refine_buffer = [&]() {
+            const long long t0 = timing ? clock64() : 0;
+            double th = CUDART_INF;
+            for (uint32_t idx = lane; idx < ncand; idx += 32) {
+                Cand c = cand[idx];
+                if (c.k & kRefinedBit) continue;
+                const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
+                const uint32_t K = s_c1[i], n = P.c2[j], k = c.k;
+                const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
+                double a = (double)(K - k), b = (double)(n - k);
+                double cc = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
+                double t = 1.0, S = 1.0;
+                // pmf(k+1)/pmf(k) = a b / (cc d); then a, b fall and cc, d rise by one per step
+                while (a > 0.0 && b > 0.0) {
+                    t *= (a * b) / (cc * d);
+                    S += t;
+                    if (t < S * 0x1p-53 && (a * b) < (cc * d)) break;
+                    a -= 1.0;
+                    b -= 1.0;
+                    cc += 1.0;
+                    d += 1.0;
+                }
+                const double lp = s + log(S);
+                if (task == P.debug_task && n_refine < 4000 && (n_refine % 40) == 0)
+                    printf("refine i=%u j=%u K=%u n=%u k=%u level=%d theta=%.4f s=%.4f lp=%.4f oldv=%.4f meta=(%u,%u,%u)\n", i, j, K, n, k, level, theta, s, lp, c.v,
+                           P.cellmeta[(size_t)i * P.T2 + j].x, P.cellmeta[(size_t)i * P.T2 + j].y & 0xFFFFu, P.cellmeta[(size_t)i * P.T2 + j].y >> 16);
+                c.v = lp - kRefineEps + kEps;
+                c.k |= kRefinedBit;
+                cand[idx] = c;
+                th = fmin(th, lp + kRefineEps);
+                ++n_refine;
+            }
+            theta = fmin(theta, warp_min(th));
+            __syncwarp();
+            if (timing) tm_refine += clock64() - t0;
+        };
+
+        // (4) statrs-order FP64 tail for every buffered candidate, one per lane; empties the buffer and
+        //     tightens theta to the exact minimum seen so far
+        auto evaluate_buffer = [&]() {
+            const long long t0 = timing ? clock64() : 0;
+            double th = CUDART_INF;
+            for (uint32_t idx = lane; idx < ncand; idx += 32) {
+                const Cand c = cand[idx];
+                const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
+                Best b;
+                b.k = c.k & ~kRefinedBit;
+                b.p = hypergeom_pvalue_exact(P.lf, P.N, s_c1[i], P.c2[j], b.k);
+                b.ij = c.ij;
+                merge_exact(P, s_c1, ex, b, false);
+                th = fmin(th, b.p > 0.0 ? log(b.p) + kEps : kZeroHi);
+            }
+            n_eval += ncand;
+            theta = fmin(theta, warp_min(th));
+            ncand = 0;
+            __syncwarp();
+            if (timing) tm_eval += clock64() - t0;
+        };
 
         // drains the queue of cells that passed the critical-overlap screen, 32 at a time
         auto drain = [&](bool flush) {
+            const long long t0 = timing ? clock64() : 0;
             uint32_t qc = *qcnt;
             while (qc >= 32 || (flush && qc > 0)) {
                 const uint32_t take = qc < 32 ? qc : 32;
@@ -398,32 +547,47 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__
                     e.k = Qk[start + lane];
                     const uint32_t i = e.ij >> 16, j = e.ij & 0xFFFFu;
                     const uint32_t K = s_c1[i], n = P.c2[j], k = e.k;
-                    const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
-                    const double a = (double)(K - k), b = (double)(n - k);
-                    const double c = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
-                    const double r1 = (a * b) / (c * d);  // pmf(k+1) / pmf(k)
-                    if (r1 < 1.0 && s < kZeroLo) {
-                        // every tail term underflows: the reference's p is exactly 0.0 -> integer tie-break only
-                        Best z;
-                        z.p = 0.0;
-                        z.k = k;
-                        z.ij = e.ij;
-                        if (better(z, zero)) zero = z;
-                        ub = kZeroHi - kEps;
-                    } else {
-                        double lb = s;  // p >= pmf(k)
-                        if (r1 < 1.0) {
-                            ub = s - log1p(-r1);  // ratios fall with k: p <= pmf(k) / (1 - r1)
-                            // ratios over the next mm steps are all >= r_mm: p >= pmf * (1 - r^(mm+1)) / (1 - r)
-                            double mm = floor(1.0 / (1.0 - r1)) + 1.0;
-                            mm = fmin(mm, fmin(a, b));
-                            if (mm >= 1.0) {
-                                const double rm = ((a - mm + 1.0) * (b - mm + 1.0)) / ((c + mm - 1.0) * (d + mm - 1.0));
-                                if (rm > 0.0 && rm < 1.0) lb = s + log((1.0 - exp((mm + 1.0) * log(rm))) / (1.0 - rm));
-                            }
-                        }
-                        e.v = lb;
+                    const uint2 meta = P.cellmeta[(size_t)i * P.T2 + j];
+                    const uint32_t dk = k - (meta.y & 0xFFFFu);
+                    if (dk < (meta.y >> 16)) {
+                        // tabulated: log p of this (cell, k) to ~1e-10, no arithmetic at all
+                        const double lp = P.lptab[meta.x + dk];
+                        ub = lp + kRefineEps - kEps;
+                        e.v = lp - kRefineEps + kEps;
+                        e.k |= kRefinedBit;
                         keep = true;
+                    } else if (k < (meta.y & 0xFFFFu)) {
+                        // below the tabulated range: the table build certified p(kbase - 1) > tau_1, and p falls with k
+                        e.v = P.level_log[1];
+                        keep = true;
+                    } else {
+                        const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
+                        const double a = (double)(K - k), b = (double)(n - k);
+                        const double c = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
+                        const double r1 = (a * b) / (c * d);  // pmf(k+1) / pmf(k)
+                        if (r1 < 1.0 && s < kZeroLo) {
+                            // every tail term underflows: the reference's p is exactly 0.0 -> integer tie-break only
+                            Best z;
+                            z.p = 0.0;
+                            z.k = k;
+                            z.ij = e.ij;
+                            if (better(z, zero)) zero = z;
+                            ub = kZeroHi - kEps;
+                        } else {
+                            double lb = s;  // p >= pmf(k)
+                            if (r1 < 1.0) {
+                                ub = s - log1p(-r1);  // ratios fall with k: p <= pmf(k) / (1 - r1)
+                                // ratios over the next mm steps are all >= r_mm: p >= pmf * (1 - r^(mm+1)) / (1 - r)
+                                double mm = floor(2.0 / (1.0 - r1)) + 1.0;
+                                mm = fmin(mm, fmin(a, b));
+                                if (mm >= 1.0) {
+                                    const double rm = ((a - mm + 1.0) * (b - mm + 1.0)) / ((c + mm - 1.0) * (d + mm - 1.0));
+                                    if (rm > 0.0 && rm < 1.0) lb = s + log((1.0 - exp((mm + 1.0) * log(rm))) / (1.0 - rm));
+                                }
+                            }
+                            e.v = lb;
+                            keep = true;
+                        }
                     }
                 }
                 theta = fmin(theta, warp_min(ub + kEps));
@@ -432,24 +596,45 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__
                 const uint32_t add = __popc(bal);
                 if (ncand + add > cap) {
                     ncand = compact_cands(cand, ncand, theta, lane);
-                    if (ncand + add > cap) overflow = true;
+                    if (ncand + add > cap) {  // still full: sharpen the survivors' bounds, then drop the beaten ones
+                        refine_buffer();
+                        ncand = compact_cands(cand, ncand, theta, lane);
+                    }
+                    if (ncand + add > cap) evaluate_buffer();  // genuinely full of near-ties: settle them exactly
+                    keep = keep && (e.v - kEps <= theta);
                 }
-                if (!overflow) {
-                    if (keep) cand[ncand + __popc(bal & lt)] = e;
-                    ncand += add;
-                }
+                const unsigned bal2 = __ballot_sync(kFull, keep);
+                if (keep) cand[ncand + __popc(bal2 & lt)] = e;
+                ncand += __popc(bal2);
                 __syncwarp();
                 n_level2 += take;
+                ++n_drain_iter;
                 qc = start;
             }
             if (lane == 0) *qcnt = qc;
             __syncwarp();
             while (level < P.levels && theta <= P.level_log[level + 1]) ++level;
+            if (timing) tm_drain += clock64() - t0;
         };
 
-        uint32_t base = 0, lo = 0;
-        uint32_t cur = row[lane], nxt = row[32 + lane];
-        for (int i = 0; i < P.T1 && !overflow; ++i) {
+        // partner-slot row staged through shared memory with cp.async: chunk c = positions [256c, 256c+256), one 16 B
+        // copy per lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)
+        const uint32_t n_chunks = P.pb_stride >> 8;
+        auto issue_chunk = [&](uint32_t c) {
+            if (c < n_chunks) {
+                const uint16_t *src = row + ((size_t)c << 8) + lane * 8;
+                const uint32_t dst = ring_addr + (((c & 3u) << 8) + lane * 8) * 2;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue_chunk(0);
+        issue_chunk(1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        issue_chunk(2);
+        uint32_t cbase = 0, lo = 0;
+        for (int i = 0; i < P.T1; ++i) {
             const uint32_t hi = s_c1[i];
             // critical overlaps of this row at the current screen level (in flight during the scatter)
             const uint16_t *__restrict__ kr = P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad + lane;
@@ -457,19 +642,25 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__
 #pragma unroll
             for (int m = 0; m < CH; ++m) kc[m] = __ldg(kr + m * 32);
             // (1) bin this row's genes: position -> partner's column slot, privatised per warp
+            const long long ts0 = timing ? clock64() : 0;
             while (lo < hi) {
-                if (lo >= base + 32) {
-                    base += 32;
-                    cur = nxt;
-                    nxt = (base + 32 + lane < P.pb_stride) ? row[base + 32 + lane] : (uint32_t)kNoSlot;
+                if ((lo >> 8) > cbase) {  // chunk cbase is consumed: cbase+2 must have landed, refill its slot
+                    ++cbase;
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    issue_chunk(cbase + 2);
                     continue;
                 }
-                const uint32_t e = hi < base + 32 ? hi : base + 32;
-                const uint32_t pos = base + lane;
-                if (pos >= lo && pos < e && cur != kNoSlot) atomicAdd(&D[cur], 1u);
+                const uint32_t e = hi < lo + 32 ? hi : lo + 32;
+                const uint32_t pos = lo + lane;
+                if (pos < e) {
+                    const uint32_t slot = ring[pos & (kRing - 1)];
+                    if (slot != kNoSlot) atomicAdd(&D[slot], 1u);
+                }
                 lo = e;
             }
             __syncwarp();
+            if (timing) tm_scatter += clock64() - ts0;
             // (2) 2-D inclusive prefix: lane-local run over its CH columns + warp exclusive scan of lane totals
             uint32_t run = 0;
 #pragma unroll
@@ -500,72 +691,57 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, const uint32_t *__
             if (*qcnt >= 32) drain(false);
         }
 
-        if (overflow) {
-            if (lane == 0) status[task] = 1;  // candidate buffer overflow: re-run with the global buffer
-            __syncwarp();
-            continue;
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         drain(true);
-        if (overflow) {
-            if (lane == 0) status[task] = 1;
-            __syncwarp();
-            continue;
-        }
         ncand = compact_cands(cand, ncand, theta, lane);
-
-        // (4) statrs-order FP64 tail for the survivors, one candidate per lane
-        Best best;
-        best.p = CUDART_INF;
-        best.k = 0;
-        best.ij = 0xFFFFFFFFu;
-        for (uint32_t idx = lane; idx < ncand; idx += 32) {
-            Cand c = cand[idx];
-            const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
-            const double p = hypergeom_pvalue_exact(P.lf, P.N, s_c1[i], P.c2[j], c.k);
-            cand[idx].v = p;
-            Best b;
-            b.p = p;
-            b.k = c.k;
-            b.ij = c.ij;
-            if (better(b, best)) best = b;
-        }
-        if (better(zero, best)) best = zero;
+        refine_buffer();
+        ncand = compact_cands(cand, ncand, theta, lane);
+        evaluate_buffer();
+        merge_exact(P, s_c1, ex, zero, false);
         // (5) warp-shuffle argmin with the reference tie-break
-        best = warp_best(best);
-        __syncwarp();
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            Best o;
+            o.p = __shfl_xor_sync(kFull, ex.best.p, off);
+            o.k = __shfl_xor_sync(kFull, ex.best.k, off);
+            o.ij = __shfl_xor_sync(kFull, ex.best.ij, off);
+            const bool o_near = __shfl_xor_sync(kFull, (int)ex.near, off) != 0;
+            merge_exact(P, s_c1, ex, o, o_near);
+        }
+        const Best best = ex.best;
         if (best.ij == 0xFFFFFFFFu || !(best.p < 1.0)) {
             // no cell beats the cells the reference short-circuits to p = 1.0: needs the dense path
             if (lane == 0) status[task] = 2;
             __syncwarp();
             continue;
         }
-        const uint32_t bi = best.ij >> 16, bj = best.ij & 0xFFFFu;
-        const uint32_t bK = s_c1[bi], bn = P.c2[bj];
-        bool near = false;
-        if (best.p > 0.0) {
-            for (uint32_t idx = lane; idx < ncand; idx += 32) {
-                const Cand c = cand[idx];
-                if (c.ij == best.ij) continue;
-                const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
-                const bool same = (s_c1[i] == bK && P.c2[j] == bn && c.k == best.k);
-                if (!same && fabs(c.v - best.p) <= 1e-12 * best.p) near = true;
-            }
-        }
-        near = __any_sync(kFull, near);
         if (lane == 0) {
+            const uint32_t bi = best.ij >> 16, bj = best.ij & 0xFFFFu;
             dto_b200_record r;
             r.rank1 = P.thr1[bi];
             r.rank2 = P.thr2[bj];
-            r.set1_len = bK;
-            r.set2_len = bn;
+            r.set1_len = s_c1[bi];
+            r.set2_len = P.c2[bj];
             r.intersection_size = best.k;
-            r.flags = record_flags | (near ? DTO_B200_FLAG_NEAR_TIE : 0u) | (WIDE ? DTO_B200_FLAG_PATH_WIDE : 0u);
+            r.flags = record_flags | (ex.near ? DTO_B200_FLAG_NEAR_TIE : 0u);
             r.population_size = P.N;
             r.pvalue = best.p;
             out[task] = r;
             status[task] = 0;
-            atomicAdd(&counters[0], (unsigned long long)ncand);
+            atomicAdd(&counters[0], n_eval);
             atomicAdd(&counters[1], n_level2);
+            atomicAdd(&counters[2], n_refine);
+            if (task_stats) {
+                uint32_t *ts = task_stats + (size_t)kTaskStatWords * task;
+                ts[0] = (uint32_t)n_level2;
+                ts[1] = (uint32_t)n_refine;
+                ts[2] = (uint32_t)n_eval;
+                ts[3] = (uint32_t)((clock64() - t_begin) >> 4);
+                ts[4] = (uint32_t)(tm_scatter >> 4);
+                ts[5] = (uint32_t)(tm_drain >> 4);
+                ts[6] = (uint32_t)(tm_refine >> 4);
+                ts[7] = (uint32_t)(tm_eval >> 4);
+            }
         }
         __syncwarp();
     }
@@ -683,29 +859,26 @@ __global__ void hbm_copy_probe_kernel(const uint4 *__restrict__ src, uint4 *__re
 // =====================================================================================================
 // launchers
 // =====================================================================================================
-template <int CH, bool WIDE>
-static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
-                                 uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
-                                 unsigned long long *counters, int grid, int warps, cudaStream_t st) {
-    using L = ScanLayout<CH, WIDE>;
+template <int CH>
+static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags,
+                                 dto_b200_record *out, uint32_t *status, unsigned long long *counters,
+                                 uint32_t *task_stats, int grid, int warps, cudaStream_t st) {
+    using L = ScanLayout<CH>;
     const size_t smem = (((size_t)P.T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * L::per_warp;
-    auto kern = scan_kernel<CH, WIDE>;
+    auto kern = scan_kernel<CH>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, warps * 32, smem, st>>>(P, pb, task_ids, n_tasks, flags, out, status,
-                                          reinterpret_cast<Cand *>(wide_buf), counters);
+    kern<<<grid, warps * 32, smem, st>>>(P, pb, n_tasks, flags, out, status, counters, task_stats);
     return cudaGetLastError();
 }
 
-size_t scan_smem_bytes(int CH, bool wide, int T1, int warps) {
+size_t scan_smem_bytes(int CH, int T1, int warps) {
     const size_t chp = (size_t)(CH | 1);
     const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
     const size_t q = (size_t)(32 * CH + 32) * 8;
-    const size_t per = d + q + 16 + (wide ? 0 : (size_t)kCandCap * sizeof(Cand));
+    const size_t per = d + q + 16 + (size_t)kCandCap * sizeof(Cand) + (size_t)kRing * 2;
     return (((size_t)T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * per;
 }
-
-size_t cand_bytes() { return sizeof(Cand); }
 
 int pick_ch(int T2) {
     static const int opts[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 48, 64};
@@ -715,14 +888,12 @@ int pick_ch(int T2) {
     return -1;
 }
 
-template <bool WIDE>
-static cudaError_t launch_scan_w(const Problem &P, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
-                                 uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
-                                 unsigned long long *counters, int grid, int warps, cudaStream_t st) {
-#define DTO_CASE(X)                                                                                           \
-    case X:                                                                                                   \
-        return launch_scan_t<X, WIDE>(P, pb, task_ids, n_tasks, flags, out, status, wide_buf, counters, grid, \
-                                      warps, st);
+cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags, dto_b200_record *out,
+                        uint32_t *status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
+                        cudaStream_t st) {
+#define DTO_CASE(X) \
+    case X:         \
+        return launch_scan_t<X>(P, pb, n_tasks, flags, out, status, counters, task_stats, grid, warps, st);
     switch (P.CH) {
         DTO_CASE(1) DTO_CASE(2) DTO_CASE(4) DTO_CASE(8) DTO_CASE(12) DTO_CASE(16) DTO_CASE(20) DTO_CASE(24)
         DTO_CASE(28) DTO_CASE(32) DTO_CASE(48) DTO_CASE(64)
@@ -732,19 +903,21 @@ static cudaError_t launch_scan_w(const Problem &P, const uint16_t *pb, const uin
 #undef DTO_CASE
 }
 
-cudaError_t launch_scan(const Problem &P, bool wide, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
-                        uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
-                        unsigned long long *counters, int grid, int warps, cudaStream_t st) {
-    return wide ? launch_scan_w<true>(P, pb, task_ids, n_tasks, flags, out, status, wide_buf, counters, grid, warps, st)
-                : launch_scan_w<false>(P, pb, task_ids, n_tasks, flags, out, status, wide_buf, counters, grid, warps, st);
-}
-
-cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, cudaStream_t st) {
+cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *counts, uint2 *meta, cudaStream_t st) {
     const size_t bytes = (size_t)(P.levels + 1) * P.T1 * P.T2pad * sizeof(uint16_t);
     cudaError_t e = cudaMemsetAsync(kcrit, 0xFF, bytes, st);
     if (e != cudaSuccess) return e;
     const int cells = P.T1 * P.T2;
-    build_kcrit_kernel<<<(cells + 255) / 256, 256, 0, st>>>(P, kcrit);
+    e = cudaMemsetAsync(meta, 0, (size_t)cells * sizeof(uint2), st);
+    if (e != cudaSuccess) return e;
+    build_kcrit_kernel<<<(cells + 255) / 256, 256, 0, st>>>(P, kcrit, 0, counts, meta, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *meta, double *lptab, cudaStream_t st) {
+    const int cells = P.T1 * P.T2;
+    set_meta_offsets_kernel<<<(cells + 255) / 256, 256, 0, st>>>(cells, offsets, meta);
+    build_kcrit_kernel<<<(cells + 255) / 256, 256, 0, st>>>(P, nullptr, 1, nullptr, meta, lptab);
     return cudaGetLastError();
 }
 

@@ -8,21 +8,23 @@ namespace dto {
 constexpr int kScanThreads = 256;   // max threads per CTA of the scan kernel (8 warps = 8 permutations)
 constexpr int kSigmaThreads = 1024; // one CTA per permutation in the pairing kernel
 constexpr int kCandCap = 256;       // per-warp shared-memory candidate buffer (entries)
+constexpr int kTaskStatWords = 8;   // per-task diagnostics words (option task_stats)
+constexpr int kRing = 1024;         // per-warp staging ring of partner slots (u16), 4 cp.async chunks of 256
 
 int pick_ch(int T2);
 int pick_bucket_bits(uint32_t n);
-size_t scan_smem_bytes(int CH, bool wide, int T1, int warps);
+size_t scan_smem_bytes(int CH, int T1, int warps);
 size_t sigma_smem_bytes(const Problem &P, int B1, int B2);
-size_t cand_bytes();
 
-cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, cudaStream_t st);
+cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *counts, uint2 *meta, cudaStream_t st);
+cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *meta, double *lptab, cudaStream_t st);
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
                               uint32_t *pairing_out, int grid, cudaStream_t st);
 cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, int n_tasks,
                            uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st);
-cudaError_t launch_scan(const Problem &P, bool wide, const uint16_t *pb, const uint32_t *task_ids, int n_tasks,
-                        uint32_t flags, dto_b200_record *out, uint32_t *status, void *wide_buf,
-                        unsigned long long *counters, int grid, int warps, cudaStream_t st);
+cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags, dto_b200_record *out,
+                        uint32_t *status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
+                        cudaStream_t st);
 cudaError_t launch_full_grid(const Problem &P, const uint16_t *pbrow, uint32_t *H, double *pv, double *logp,
                              cudaStream_t st);
 cudaError_t launch_full_argmin(const Problem &P, const uint32_t *H, const double *pv, uint32_t flags,

@@ -140,6 +140,14 @@ class Engine:
         capi.check(capi.lib().dto_b200_get_stats(self._ctx, C.byref(s)))
         return {f: getattr(s, f) for f, _ in s._fields_}
 
+    def last_batch_task_stats(self, max_tasks: int = 1 << 20) -> np.ndarray:
+        """(n, 8) uint32 per task of the last launch: screened, refined, exact cells; cycles/16 of task, scatter, drain,
+        refine, exact stages."""
+        out = np.zeros((max_tasks, 8), dtype=np.uint32)
+        n = C.c_size_t()
+        capi.check(capi.lib().dto_b200_last_batch_task_stats(self._ctx, capi.ptr(out, C.c_uint32), max_tasks, C.byref(n)))
+        return out[: n.value]
+
     def reset_stats(self):
         capi.check(capi.lib().dto_b200_reset_stats(self._ctx))
 

@@ -49,7 +49,6 @@ typedef struct dto_b200_record {
 #define DTO_B200_FLAG_PERMUTED 0x1u  /* record.permuted */
 #define DTO_B200_FLAG_NEAR_TIE 0x2u  /* another cell with different (K,n,k) lies within 1e-12 relative of the minimum: the \
                                         reference's pick between them is decided by last-ulp noise of its libm exp() */
-#define DTO_B200_FLAG_PATH_WIDE 0x4u /* solved by the wide (global-buffer) kernel */
 #define DTO_B200_FLAG_PATH_FULL 0x8u /* solved by the full-grid exact pipeline */
 
 typedef struct dto_b200_ctx dto_b200_ctx;
@@ -116,20 +115,29 @@ int dto_b200_hypergeometric_pvalues(dto_b200_ctx *ctx, const uint64_t *N, const 
                                     const uint64_t *k, size_t count, double *pvalue_out);
 
 typedef struct dto_b200_stats {
-    uint64_t tasks_fast;        /* tasks solved by the warp-per-permutation kernel */
-    uint64_t tasks_wide;        /* re-run with the global candidate buffer (overflow) */
+    uint64_t tasks_fast;        /* tasks solved by the warp-per-permutation scan kernel */
     uint64_t tasks_full;        /* re-run through the full-grid exact pipeline (min p >= 1 / no candidate) */
     uint64_t candidates;        /* cells evaluated exactly (statrs-order tail) */
     uint64_t level2_cells;      /* cells that passed the critical-overlap screen */
+    uint64_t refined_cells;     /* cells whose tail was summed by the ratio recurrence (log p to ~1e-10) */
     uint64_t kernel_launches;   /* launches of this library's kernels since create/reset */
     double last_scan_kernel_ms; /* CUDA-event time of the scan kernel launches of the last run call (sum) */
     double last_sigma_kernel_ms;
     uint64_t last_scan_launches;
+    double last_run_ms;         /* CUDA-event time of the whole last run_permuted_* call on the library's stream */
+    uint64_t h2d_bytes;         /* bytes copied host->device since create/reset (inputs, tables, task lists) */
+    uint64_t d2h_bytes;         /* bytes copied device->host since create/reset (records, status words) */
+    uint64_t lptab_entries;     /* size of the per-problem log-p lookup table (8 B each) */
 } dto_b200_stats;
 int dto_b200_get_stats(dto_b200_ctx *ctx, dto_b200_stats *out);
 int dto_b200_reset_stats(dto_b200_ctx *ctx);
 
-/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels", "cipher_rounds" */
+/* diagnostics: per-task {screened cells, recurrence-refined cells, exactly evaluated cells, then SM cycles / 16 of:
+ * the whole task, the histogram scatter, the screen-queue drain, the refine stage, the exact stage} of the LAST scan
+ * launch; needs option "task_stats" = 1.  out holds 8 u32 per task. */
+int dto_b200_last_batch_task_stats(dto_b200_ctx *ctx, uint32_t *out, size_t max_tasks, size_t *n_out);
+
+/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" (before set_problem), "task_stats" */
 int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value);
 
 /* micro-probes used by bench.py for roofline denominators (measured live, not assumed) */

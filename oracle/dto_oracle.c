@@ -334,10 +334,24 @@ int oracle_process_threshold_pairs_faithful(const char *const *ids1, const uint3
                                             const uint32_t *thr2, size_t T2,
                                             const uint32_t *perm1, const uint32_t *perm2, int permuted_flag,
                                             uint64_t population, oracle_record_t *out) {
+    return oracle_process_threshold_pairs_faithful_sampled(ids1, ranks1, n1, thr1, T1, ids2, ranks2, n2, thr2, T2, perm1,
+                                                           perm2, permuted_flag, population, 1, out);
+}
+
+/* Same loop restricted to rows i % row_stride == 0 (records of skipped rows are left untouched): a bounded,
+ * evenly spread SAMPLE of the reference's work, used only to time the CPU baseline at sizes where one full
+ * task costs minutes (bench.py says so in cpu_baseline.sample). row_stride == 1 is the full reference loop. */
+int oracle_process_threshold_pairs_faithful_sampled(const char *const *ids1, const uint32_t *ranks1, size_t n1,
+                                                    const uint32_t *thr1, size_t T1,
+                                                    const char *const *ids2, const uint32_t *ranks2, size_t n2,
+                                                    const uint32_t *thr2, size_t T2,
+                                                    const uint32_t *perm1, const uint32_t *perm2, int permuted_flag,
+                                                    uint64_t population, size_t row_stride, oracle_record_t *out) {
+    if (row_stride == 0) row_stride = 1;
     featvec_t *cache = (featvec_t *)calloc(T2 ? T2 : 1, sizeof(featvec_t));
     unsigned char *have = (unsigned char *)calloc(T2 ? T2 : 1, 1);
     int rc = 0;
-    for (size_t i = 0; i < T1 && rc == 0; ++i) {
+    for (size_t i = 0; i < T1 && rc == 0; i += row_stride) {
         featvec_t g1 = feature_set_by_threshold(ids1, ranks1, n1, perm1, thr1[i]);
         for (size_t j = 0; j < T2; ++j) {
             if (!have[j]) { /* feature_sets_cache.entry(threshold2).or_insert_with (process_threshold_pairs.rs:92-98) */
@@ -485,6 +499,21 @@ int oracle_grid_int(const uint32_t *ranks1, size_t n1, const uint32_t *thr1, siz
     return rc;
 }
 
+/* SURVEY 8(d) accounting: sum over cells of R (tail terms to converge to 2^-53) and the number of cells the
+ * reference does not short-circuit, for a given overlap grid. */
+void oracle_grid_tail_terms(const uint32_t *overlap, const uint32_t *c1, size_t T1, const uint32_t *c2, size_t T2,
+                            uint64_t population, const double *lf, uint64_t *terms_out, uint64_t *evaluated_cells_out) {
+    uint64_t terms = 0, cells = 0;
+    for (size_t i = 0; i < T1; ++i)
+        for (size_t j = 0; j < T2; ++j) {
+            uint64_t r = oracle_tail_terms(lf, population, c1[i], c2[j], overlap[i * T2 + j]);
+            terms += r;
+            cells += r > 0;
+        }
+    *terms_out = terms;
+    *evaluated_cells_out = cells;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * epilogue
  * ---------------------------------------------------------------------------------------------- */
@@ -589,6 +618,7 @@ typedef struct {
     size_t begin, end;
     uint64_t seed;
     int mode;
+    size_t row_stride;
     oracle_record_t *results;
     int rc;
 } chunk_job_t;
@@ -607,15 +637,23 @@ static void *chunk_main(void *arg) {
         shuffle_with(perm2, J->n2, &r);
         int permute = J->task_permute[t] != 0;
         if (J->mode == 0) {
-            int rc = oracle_process_threshold_pairs_faithful(J->ids1, J->ranks1, J->n1, J->thr1, J->T1,
-                                                             J->ids2, J->ranks2, J->n2, J->thr2, J->T2,
-                                                             permute ? perm1 : NULL, permute ? perm2 : NULL, permute,
-                                                             J->population, grid);
+            int rc = oracle_process_threshold_pairs_faithful_sampled(J->ids1, J->ranks1, J->n1, J->thr1, J->T1,
+                                                                     J->ids2, J->ranks2, J->n2, J->thr2, J->T2,
+                                                                     permute ? perm1 : NULL, permute ? perm2 : NULL,
+                                                                     permute, J->population, J->row_stride, grid);
             if (rc) {
                 J->rc = rc;
                 break;
             }
-            J->results[t] = grid[oracle_argmin_tiebreak(grid, J->T1 * J->T2)];
+            if (J->row_stride > 1) { /* compact the sampled rows before the reduction */
+                size_t rows = 0;
+                for (size_t i = 0; i < J->T1; i += J->row_stride, ++rows)
+                    if (rows * J->row_stride != rows)
+                        memmove(&grid[rows * J->T2], &grid[i * J->T2], J->T2 * sizeof(oracle_record_t));
+                J->results[t] = grid[oracle_argmin_tiebreak(grid, rows * J->T2)];
+            } else {
+                J->results[t] = grid[oracle_argmin_tiebreak(grid, J->T1 * J->T2)];
+            }
         } else {
             int rc = oracle_grid_int(J->ranks1, J->n1, J->thr1, J->T1, J->ranks2, J->n2, J->thr2, J->T2,
                                      J->slot2_of_1, permute ? perm1 : NULL, permute ? perm2 : NULL, permute,
@@ -637,6 +675,15 @@ int oracle_run_single_node(const char *const *ids1, const uint32_t *ranks1, size
                            const int32_t *slot2_of_1, uint64_t population,
                            const uint8_t *task_permute, size_t n_tasks, size_t num_threads,
                            uint64_t seed, int mode, oracle_record_t *results_out) {
+    return oracle_run_single_node_sampled(ids1, ranks1, n1, ids2, ranks2, n2, slot2_of_1, population, task_permute,
+                                          n_tasks, num_threads, seed, mode, 1, results_out);
+}
+
+int oracle_run_single_node_sampled(const char *const *ids1, const uint32_t *ranks1, size_t n1,
+                                   const char *const *ids2, const uint32_t *ranks2, size_t n2,
+                                   const int32_t *slot2_of_1, uint64_t population,
+                                   const uint8_t *task_permute, size_t n_tasks, size_t num_threads,
+                                   uint64_t seed, int mode, size_t row_stride, oracle_record_t *results_out) {
     if (n_tasks == 0) return 0;
     if (num_threads == 0) num_threads = 1; /* main.rs:73-76 */
     size_t T1 = oracle_generate_thresholds(ranks1, n1, NULL, 0);
@@ -663,7 +710,7 @@ int oracle_run_single_node(const char *const *ids1, const uint32_t *ranks1, size
         J->task_permute = task_permute;
         J->begin = c * chunk;
         J->end = (c + 1) * chunk < n_tasks ? (c + 1) * chunk : n_tasks;
-        J->seed = seed; J->mode = mode; J->results = results_out; J->rc = 0;
+        J->seed = seed; J->mode = mode; J->row_stride = row_stride ? row_stride : 1; J->results = results_out; J->rc = 0;
         pthread_create(&th[c], NULL, chunk_main, J);
     }
     int rc = 0;

@@ -73,6 +73,14 @@ int oracle_process_threshold_pairs_faithful(const char *const *ids1, const uint3
                                             const uint32_t *perm1, const uint32_t *perm2, int permuted_flag,
                                             uint64_t population, oracle_record_t *records_out);
 
+/* rows i % row_stride == 0 only: bounded sample for timing (see dto_oracle.c) */
+int oracle_process_threshold_pairs_faithful_sampled(const char *const *ids1, const uint32_t *ranks1, size_t n1,
+                                                    const uint32_t *thr1, size_t T1,
+                                                    const char *const *ids2, const uint32_t *ranks2, size_t n2,
+                                                    const uint32_t *thr2, size_t T2,
+                                                    const uint32_t *perm1, const uint32_t *perm2, int permuted_flag,
+                                                    uint64_t population, size_t row_stride, oracle_record_t *records_out);
+
 /* optimize's reduction (dto/optimize_main.rs:73-116) over a row-major record vector. Returns index of the winner. */
 size_t oracle_argmin_tiebreak(const oracle_record_t *records, size_t count);
 
@@ -100,6 +108,15 @@ int oracle_run_single_node(const char *const *ids1, const uint32_t *ranks1, size
                            const int32_t *slot2_of_1, uint64_t population,
                            const uint8_t *task_permute, size_t n_tasks, size_t num_threads,
                            uint64_t seed, int mode, oracle_record_t *results_out);
+
+int oracle_run_single_node_sampled(const char *const *ids1, const uint32_t *ranks1, size_t n1,
+                                   const char *const *ids2, const uint32_t *ranks2, size_t n2,
+                                   const int32_t *slot2_of_1, uint64_t population,
+                                   const uint8_t *task_permute, size_t n_tasks, size_t num_threads,
+                                   uint64_t seed, int mode, size_t row_stride, oracle_record_t *results_out);
+
+void oracle_grid_tail_terms(const uint32_t *overlap, const uint32_t *c1, size_t T1, const uint32_t *c2, size_t T2,
+                            uint64_t population, const double *lf, uint64_t *terms_out, uint64_t *evaluated_cells_out);
 
 /* uniform Fisher-Yates in rand 0.8.5's loop order (for i in (1..n).rev() swap(i, gen_range(0..=i))) */
 void oracle_shuffle(uint32_t *idx, size_t n, uint64_t seed);

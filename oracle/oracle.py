@@ -119,6 +119,14 @@ def lib():
         strp, u32p, C.c_size_t, strp, u32p, C.c_size_t, i32p, C.c_uint64,
         C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_uint64, C.c_int, recp,
     ]
+    L.oracle_run_single_node_sampled.restype = C.c_int
+    L.oracle_run_single_node_sampled.argtypes = [
+        strp, u32p, C.c_size_t, strp, u32p, C.c_size_t, i32p, C.c_uint64,
+        C.POINTER(C.c_uint8), C.c_size_t, C.c_size_t, C.c_uint64, C.c_int, C.c_size_t, recp,
+    ]
+    L.oracle_grid_tail_terms.restype = None
+    L.oracle_grid_tail_terms.argtypes = [u32p, u32p, C.c_size_t, u32p, C.c_size_t, C.c_uint64, f64p,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.oracle_shuffle.restype = None
     L.oracle_shuffle.argtypes = [u32p, C.c_size_t, C.c_uint64]
     _lib = L
@@ -308,22 +316,36 @@ def grid_int(l1, l2, population, slot2_of_1=None, perm1=None, perm2=None, lf=Non
     return GridResult(ov, pp, lp, best.as_dict())
 
 
-def run_single_node(l1, l2, population, task_permute, num_threads, seed=0, mode=0, slot2_of_1=None) -> np.ndarray:
-    """run/single_node.rs:83-137 (static chunks on OS threads); mode 0 = reference-faithful, 1 = integer."""
+def run_single_node(l1, l2, population, task_permute, num_threads, seed=0, mode=0, slot2_of_1=None, row_stride=1) -> np.ndarray:
+    """run/single_node.rs:83-137 (static chunks on OS threads); mode 0 = reference-faithful, 1 = integer.
+    row_stride > 1 (faithful mode only) evaluates every row_stride-th t1 row: a bounded timing sample."""
     tp = np.ascontiguousarray(task_permute, dtype=np.uint8)
     out = np.zeros(tp.size, dtype=RECORD_DTYPE)
     if slot2_of_1 is None and mode != 0:
         slot2_of_1 = slot_map(l1, l2)
     sm = None if slot2_of_1 is None else np.ascontiguousarray(slot2_of_1, dtype=np.int32)
     ids1, ids2 = _strs(l1.ids), _strs(l2.ids)
-    rc = lib().oracle_run_single_node(
+    rc = lib().oracle_run_single_node_sampled(
         ids1, _p(l1.ranks, C.c_uint32), len(l1.ids), ids2, _p(l2.ranks, C.c_uint32), len(l2.ids),
-        _p(sm, C.c_int32), population, _p(tp, C.c_uint8), tp.size, num_threads, seed, mode,
+        _p(sm, C.c_int32), population, _p(tp, C.c_uint8), tp.size, num_threads, seed, mode, row_stride,
         out.ctypes.data_as(C.POINTER(Record)),
     )
     if rc != 0:
         raise ValueError(f"oracle_run_single_node failed rc={rc}")
     return out
+
+
+def grid_tail_terms(l1, l2, population, overlap, lf=None):
+    """(sum of converged tail lengths R, number of cells the reference actually evaluates) -- SURVEY 8(d)."""
+    if lf is None:
+        lf = ln_factorial_table(population)
+    c1 = np.searchsorted(l1.ranks, l1.thresholds, side="right").astype(np.uint32)
+    c2 = np.searchsorted(l2.ranks, l2.thresholds, side="right").astype(np.uint32)
+    ov = np.ascontiguousarray(overlap, dtype=np.uint32)
+    terms, cells = C.c_uint64(), C.c_uint64()
+    lib().oracle_grid_tail_terms(_p(ov, C.c_uint32), _p(c1, C.c_uint32), c1.size, _p(c2, C.c_uint32), c2.size,
+                                 population, _p(lf, C.c_double), C.byref(terms), C.byref(cells))
+    return terms.value, cells.value
 
 
 def final_json(results: np.ndarray) -> dict:
