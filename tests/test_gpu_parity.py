@@ -287,3 +287,96 @@ def test_cli_end_to_end(built):
     assert out["rank1"] == 24 and out["rank2"] == 13 and out["unpermuted_intersection_size"] == 12 and out["fdr"] == 0.0
     assert '"unpermuted_pvalue": 0.15632183908046102' in r.stdout and '"fdr": 0.0' in r.stdout
     assert "Permutations: 5" in r.stderr and "threshold lists" in r.stderr and ": 900" in r.stderr
+
+
+def test_committed_golden_vectors(engine):
+    """tests/golden/oracle_vectors.json (tools/make_golden.py): committed fixtures, independent of the oracle build."""
+    import json
+    import os
+
+    V = json.load(open(os.path.join(H.GOLDEN, "oracle_vectors.json")))
+    for c in V["cases"]:
+        ids1, r1, ids2, r2, bg = CASES[c["name"]]()
+        l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+        assert (l1.thresholds().size, l2.thresholds().size) == (c["T1"], c["T2"])
+        assert [int(x) for x in l1.thresholds()[-3:]] == c["thresholds1_tail"]
+        engine.load_lists(l1, l2, c["population"])
+        ov, pv, _ = engine.grid_debug()
+        assert int(ov.astype(np.uint64).sum()) == c["overlap_checksum"]
+        assert float(pv[-1, -1]) == pytest.approx(float.fromhex(c["p_hex_corner"]), rel=1e-13, abs=0)
+        H.assert_record_matches(engine.run_unpermuted(), c["unpermuted_best"])
+        P = len(c["permuted_best"])
+        p1, p2 = H.perms(len(ids1), P, c["perm_seed"]), H.perms(len(ids2), P, c["perm_seed"] + 1)
+        recs = engine.run_permuted_indices(p1, p2)
+        for t in range(P):
+            if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+                H.assert_record_matches(recs[t], c["permuted_best"][t])
+
+
+def test_full_size_properties_c3(engine):
+    """BASELINE configs[2] (N = 20 000, 589 x 589) at scale, through size-independent properties:
+    determinism across batch sizes (checksum of records), every record self-consistent under re-evaluation on
+    the device, minimum really minimal against the dense grid, set sizes = #{ranks <= threshold}."""
+    N, P = 20000, 30000
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, N, 0.25)
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    engine.load_lists(l1, l2, N)
+    assert engine.shape[:2] == (589, 589)
+    engine.reset_stats()
+    engine.set_option("batch", 0)
+    a = engine.run_permuted_philox(20000, 0, P)
+    engine.set_option("batch", 4099)
+    b = engine.run_permuted_philox(20000, 0, P)
+    engine.set_option("batch", 0)
+    assert np.array_equal(a, b)
+    st = engine.stats()
+    assert st["tasks_full"] == 0
+    # re-evaluate every record's p from its own (N, K, n, k) with the standalone device kernel
+    p = engine.hypergeometric_pvalues(np.full(P, N), a["set1_len"], a["set2_len"], a["intersection_size"])
+    assert np.array_equal(p, a["pvalue"])
+    t1, t2 = l1.thresholds(), l2.thresholds()
+    assert np.array_equal(a["set1_len"], np.searchsorted(l1.ranks(), a["rank1"], side="right"))
+    assert np.array_equal(a["set2_len"], np.searchsorted(l2.ranks(), a["rank2"], side="right"))
+    assert np.all(np.isin(a["rank1"], t1)) and np.all(np.isin(a["rank2"], t2))
+    assert np.all((a["pvalue"] > 0) & (a["pvalue"] < 0.5))
+    # the dense grid of a few of these permutations: the record is the argmin with the reference tie-break
+    o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+    slot = O.slot_map(o1, o2)
+    for t in (0, 777, P - 1):
+        pairing = engine.philox_pairing(20000, t)
+        assert np.array_equal(np.sort(pairing), np.arange(N))
+        p1, p2 = H.perms_from_pairing(pairing, slot, N)
+        ov, pv, _ = engine.grid_debug(p1, p2)
+        i, j = np.unravel_index(np.argmin(pv), pv.shape)
+        assert pv[i, j] == a[t]["pvalue"]
+        if not int(a[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            assert (int(t1[i]), int(t2[j]), int(ov[i, j])) == (int(a[t]["rank1"]), int(a[t]["rank2"]), int(a[t]["intersection_size"]))
+    # null calibration: P(min p <= x) is monotone and the empirical p of the null median is ~0.5
+    med = np.median(a["pvalue"])
+    assert abs(float((a["pvalue"] <= med).mean()) - 0.5) < 0.01
+
+
+def test_background_subset_config_c5_small(engine):
+    """configs[4] semantics at reduced size: lists filtered to a background subset keep their original ranks
+    (gaps), population = |background| (hard part 5)."""
+    rng = np.random.default_rng(60000)
+    U, B = 3000, 2000
+    uni = H.ids_for(U, "t")
+    bg_idx = np.sort(rng.choice(U, size=B, replace=False))
+    ids1, r1, ids2, r2 = H.synthetic_pair(U, 60000, 0.3)
+    keep = set(uni[i] for i in bg_idx)
+    ids1 = [f"t{x[1:]}" for x in ids1]
+    ids2 = [f"t{x[1:]}" for x in ids2]
+    m1 = [i for i, g in enumerate(ids1) if g in keep]
+    m2 = [i for i, g in enumerate(ids2) if g in keep]
+    f1, fr1 = [ids1[i] for i in m1], r1[m1]
+    f2, fr2 = [ids2[i] for i in m2], r2[m2]
+    o1, o2, N, slot = load(engine, f1, fr1, f2, fr2, [uni[i] for i in bg_idx])
+    assert N == B and len(f1) == B
+    ref = check_grid(engine, o1, o2, N, slot)
+    H.assert_record_matches(engine.run_unpermuted(), ref.best)
+    p1, p2 = H.perms(B, 12, 5), H.perms(B, 12, 6)
+    recs = engine.run_permuted_indices(p1, p2)
+    for t in range(12):
+        if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            H.assert_record_matches(recs[t], O.grid_int(o1, o2, N, slot, p1[t], p2[t], want_overlap=False, want_p=False).best)
