@@ -138,11 +138,12 @@ int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags) {
     CUDA_TRY(ctx->h_status.ensure((size_t)n * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_status.p, 0xFF, (size_t)n * 4, ctx->stream));
     int warps = ctx->opt_warps;
-    while (warps > 1 && scan_smem_bytes(P.CH, P.T1, warps) > ctx->smem_optin / ((P.CH > 32) ? 1 : 2)) --warps;
+    const int ctas_per_sm = (P.CH > 32) ? 1 : kScanCtasPerSm;
+    while (warps > 1 && scan_smem_bytes(P.CH, P.T1, warps) + 1024 > (size_t)(228 * 1024) / ctas_per_sm) --warps;
     if (scan_smem_bytes(P.CH, P.T1, warps) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "scan kernel does not fit shared memory (T1=%d T2=%d)", P.T1, P.T2);
     const int ctas_needed = (n + warps - 1) / warps;
-    const int grid = std::min(ctas_needed, ctx->sm_count * 2);
+    const int grid = std::min(ctas_needed, ctx->sm_count * ctas_per_sm);
     if (ctx->opt_task_stats) {
         CUDA_TRY(ctx->d_tstats.ensure((size_t)n * 4 * kTaskStatWords));
         CUDA_TRY(cudaMemsetAsync(ctx->d_tstats.p, 0, (size_t)n * 4 * kTaskStatWords, ctx->stream));
@@ -387,7 +388,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
                     "(%llu)",
                     c1[T1 - 1], c2[T2 - 1], (unsigned long long)population);
     P.n1_eff = c1[T1 - 1];
-    P.pb_stride = ((P.n1_eff + 1 + 255) / 256) * 256;  // whole 256-position chunks (cp.async staging in the scan)
+    P.pb_stride = ((P.n1_eff + 1 + 255) / 256) * 256;  // whole staging chunks (cp.async in the scan), 512 B aligned rows
     std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(n2 ? n2 : 1);
     for (size_t j = 0; j < n1; ++j) {
         const size_t b = std::lower_bound(thr1, thr1 + T1, ranks1[j]) - thr1;

@@ -349,47 +349,44 @@ __global__ void compose_pairing_kernel(const Problem P, const uint32_t *__restri
 // K1: scan kernel
 // =====================================================================================================
 struct __align__(16) Cand {
-    uint32_t ij;
-    uint32_t k;
-    double v;  // log lower bound of p
+    uint32_t ij;  // row << 16 | column
+    uint32_t k;   // overlap | kRefinedBit
+    double v;     // log lower bound of p
 };
 
 template <int CH>
 struct ScanLayout {
     static constexpr int CHP = CH | 1;
-    static constexpr int QCAP = 32 * CH + 32;
+    static constexpr int HALF = (CH + 1) / 2;    // the screen loop checks the queue after HALF columns
+    static constexpr int QCAP = 32 * HALF + 64;  // < 32 left-overs + one half row, rounded up
     static constexpr int CAP = kCandCap;
     static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
-    static constexpr size_t q_bytes = (size_t)QCAP * 8;
-    static constexpr size_t ring_bytes = (size_t)kRing * 2;  // partner-slot staging ring (cp.async), 4 chunks of 256
+    static constexpr size_t q_bytes = ((size_t)QCAP * 6 + 15) & ~(size_t)15;  // u32 (row<<16|col) + u16 k per entry
+    static constexpr size_t ring_bytes = (size_t)kRing * 2;  // partner-slot staging ring (cp.async), 4 chunks of kChunk
     static constexpr size_t per_warp = d_bytes + q_bytes + 16 + (size_t)CAP * sizeof(Cand) + ring_bytes;
 };
-
-__device__ __forceinline__ uint32_t compact_cands(Cand *c, uint32_t n, double theta, int lane) {
-    uint32_t out = 0;
-    const unsigned lt = (1u << lane) - 1u;
-    for (uint32_t b = 0; b < n; b += 32) {
-        const uint32_t idx = b + lane;
-        Cand e;
-        bool keep = false;
-        if (idx < n) {
-            e = c[idx];
-            keep = (e.v - kEps <= theta);
-        }
-        const unsigned bal = __ballot_sync(kFull, keep);
-        __syncwarp();
-        if (keep) c[out + __popc(bal & lt)] = e;
-        out += __popc(bal);
-        __syncwarp();
-    }
-    return out;
-}
 
 // Running exact optimum of one lane / one warp, with the "near tie" witness: some OTHER (K, n, k) whose p lies
 // within 1e-12 relative of the optimum (the reference's pick between such cells hangs on the last ulp of its exp()).
 struct Exact {
     Best best;
     bool near;
+};
+
+// Per-warp state of the rare path (everything behind the screen).  Lives in local memory on purpose: the row loop
+// touches none of it, so its registers stay free for the 2 x CH column state.
+struct Rare {
+    double theta;  // certified: log(min p of the reference) <= theta
+    Exact ex;      // per-lane running optimum over everything evaluated exactly so far
+    Best zero;     // best cell on the underflow plateau (reference p == 0.0)
+    uint32_t ncand;
+    uint32_t n_level2, n_eval, n_refine;
+    const uint32_t *s_c1;
+    uint32_t *Qij;
+    uint16_t *Qk;
+    uint32_t *qcnt;
+    Cand *cand;
+    int lane;
 };
 
 __device__ __forceinline__ bool close_not_same(const Problem &P, const uint32_t *s_c1, const Best &a, const Best &b) {
@@ -410,14 +407,248 @@ __device__ __forceinline__ void merge_exact(const Problem &P, const uint32_t *s_
     }
 }
 
+__device__ __noinline__ void compact_cands(Rare &R) {
+    const int lane = R.lane;
+    Cand *c = R.cand;
+    const uint32_t n = R.ncand;
+    const double theta = R.theta;
+    uint32_t out = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t b = 0; b < n; b += 32) {
+        const uint32_t idx = b + lane;
+        Cand e;
+        bool keep = false;
+        if (idx < n) {
+            e = c[idx];
+            keep = (e.v - kEps <= theta);
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) c[out + __popc(bal & lt)] = e;
+        out += __popc(bal);
+        __syncwarp();
+    }
+    R.ncand = out;
+}
+
+// (3b) refine: tail by the ratio recurrence (no exp, no table walk) -> log p to ~1e-10 for every buffered candidate
+//      not refined yet; tightens theta so that only cells within ~1e-8 of the minimum survive
+__device__ __noinline__ void refine_buffer(const Problem &P, Rare &R) {
+    double th = CUDART_INF;
+    for (uint32_t idx = R.lane; idx < R.ncand; idx += 32) {
+        Cand c = R.cand[idx];
+        if (c.k & kRefinedBit) continue;
+        const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
+        const uint32_t K = R.s_c1[i], n = P.c2[j], k = c.k;
+        const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
+        double a = (double)(K - k), b = (double)(n - k);
+        double cc = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
+        double t = 1.0, S = 1.0;
+        // pmf(k+1)/pmf(k) = a b / (cc d); then a, b fall and cc, d rise by one per step
+        while (a > 0.0 && b > 0.0) {
+            t *= (a * b) / (cc * d);
+            S += t;
+            if (t < S * 0x1p-53 && (a * b) < (cc * d)) break;
+            a -= 1.0;
+            b -= 1.0;
+            cc += 1.0;
+            d += 1.0;
+        }
+        const double lp = s + log(S);
+        c.v = lp - kRefineEps + kEps;
+        c.k |= kRefinedBit;
+        R.cand[idx] = c;
+        th = fmin(th, lp + kRefineEps);
+        ++R.n_refine;
+    }
+    R.theta = fmin(R.theta, warp_min(th));
+    __syncwarp();
+}
+
+// (4) statrs-order FP64 tail for every buffered candidate, one per lane; empties the buffer and tightens theta to
+//     the exact minimum seen so far
+__device__ __noinline__ void evaluate_buffer(const Problem &P, Rare &R) {
+    double th = CUDART_INF;
+    for (uint32_t idx = R.lane; idx < R.ncand; idx += 32) {
+        const Cand c = R.cand[idx];
+        const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
+        Best b;
+        b.k = c.k & ~kRefinedBit;
+        b.p = hypergeom_pvalue_exact(P.lf, P.N, R.s_c1[i], P.c2[j], b.k);
+        b.ij = c.ij;
+        merge_exact(P, R.s_c1, R.ex, b, false);
+        th = fmin(th, b.p > 0.0 ? log(b.p) + kEps : kZeroHi);
+        ++R.n_eval;
+    }
+    R.theta = fmin(R.theta, warp_min(th));
+    R.ncand = 0;
+    __syncwarp();
+}
+
+// (3a) drains the queue of cells that passed the critical-overlap screen, 32 at a time: table lookup of log p (or,
+//      outside the tabulated range, certified / closed-form bounds), running bound theta, candidate buffer.
+//      Returns the screen level theta now allows.
+__device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, int level) {
+    const int lane = R.lane;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t qc = *R.qcnt;
+    while (qc >= 32 || (flush && qc > 0)) {
+        const uint32_t take = qc < 32 ? qc : 32;
+        const uint32_t start = qc - take;
+        const bool valid = (uint32_t)lane < take;
+        Cand e;
+        e.ij = 0;
+        e.k = 0;
+        e.v = CUDART_INF;
+        double ub = CUDART_INF;
+        bool keep = false;
+        if (valid) {
+            e.ij = R.Qij[start + lane];
+            e.k = R.Qk[start + lane];
+            const uint32_t i = e.ij >> 16, j = e.ij & 0xFFFFu;
+            const uint32_t K = R.s_c1[i], n = P.c2[j], k = e.k;
+            const uint2 meta = P.cellmeta[(size_t)i * P.T2 + j];
+            const uint32_t dk = k - (meta.y & 0xFFFFu);
+            if (dk < (meta.y >> 16)) {
+                // tabulated: log p of this (cell, k) to ~1e-10, no arithmetic at all
+                const double lp = P.lptab[meta.x + dk];
+                ub = lp + kRefineEps - kEps;
+                e.v = lp - kRefineEps + kEps;
+                e.k |= kRefinedBit;
+                keep = true;
+            } else if (k < (meta.y & 0xFFFFu)) {
+                // below the tabulated range: the table build certified p(kbase - 1) > tau_1, and p falls with k
+                e.v = P.level_log[1];
+                keep = true;
+            } else {
+                const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
+                const double a = (double)(K - k), b = (double)(n - k);
+                const double c = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
+                const double r1 = (a * b) / (c * d);  // pmf(k+1) / pmf(k)
+                if (r1 < 1.0 && s < kZeroLo) {
+                    // every tail term underflows: the reference's p is exactly 0.0 -> integer tie-break only
+                    Best z;
+                    z.p = 0.0;
+                    z.k = k;
+                    z.ij = e.ij;
+                    if (better(z, R.zero)) R.zero = z;
+                    ub = kZeroHi - kEps;
+                } else {
+                    double lb = s;  // p >= pmf(k)
+                    if (r1 < 1.0) {
+                        ub = s - log1p(-r1);  // ratios fall with k: p <= pmf(k) / (1 - r1)
+                        // ratios over the next mm steps are all >= r_mm: p >= pmf * (1 - r^(mm+1)) / (1 - r)
+                        double mm = floor(2.0 / (1.0 - r1)) + 1.0;
+                        mm = fmin(mm, fmin(a, b));
+                        if (mm >= 1.0) {
+                            const double rm = ((a - mm + 1.0) * (b - mm + 1.0)) / ((c + mm - 1.0) * (d + mm - 1.0));
+                            if (rm > 0.0 && rm < 1.0) lb = s + log((1.0 - exp((mm + 1.0) * log(rm))) / (1.0 - rm));
+                        }
+                    }
+                    e.v = lb;
+                    keep = true;
+                }
+            }
+        }
+        R.theta = fmin(R.theta, warp_min(ub + kEps));
+        keep = keep && (e.v - kEps <= R.theta);
+        const unsigned bal = __ballot_sync(kFull, keep);
+        if (R.ncand + __popc(bal) > (uint32_t)kCandCap) {
+            compact_cands(R);
+            if (R.ncand + __popc(bal) > (uint32_t)kCandCap) {  // still full: sharpen the survivors' bounds
+                refine_buffer(P, R);
+                compact_cands(R);
+            }
+            if (R.ncand + __popc(bal) > (uint32_t)kCandCap) evaluate_buffer(P, R);  // genuinely full of near-ties
+            keep = keep && (e.v - kEps <= R.theta);
+        }
+        const unsigned bal2 = __ballot_sync(kFull, keep);
+        if (keep) R.cand[R.ncand + __popc(bal2 & lt)] = e;
+        R.ncand += __popc(bal2);
+        __syncwarp();
+        R.n_level2 += take;
+        qc = start;
+    }
+    if (lane == 0) *R.qcnt = qc;
+    __syncwarp();
+    while (level < P.levels && R.theta <= P.level_log[level + 1]) ++level;
+    return level;
+}
+
+// (5) end of a permutation: settle what is left, warp-shuffle argmin with the reference tie-break, write the record
+__device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, int level, uint32_t record_flags,
+                                         dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
+                                         unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats,
+                                         long long t_begin) {
+    const int lane = R.lane;
+    level = drain_queue(P, R, true, level);
+    compact_cands(R);
+    refine_buffer(P, R);
+    compact_cands(R);
+    evaluate_buffer(P, R);
+    merge_exact(P, R.s_c1, R.ex, R.zero, false);
+    Exact ex = R.ex;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Best o;
+        o.p = __shfl_xor_sync(kFull, ex.best.p, off);
+        o.k = __shfl_xor_sync(kFull, ex.best.k, off);
+        o.ij = __shfl_xor_sync(kFull, ex.best.ij, off);
+        const bool o_near = __shfl_xor_sync(kFull, (int)ex.near, off) != 0;
+        merge_exact(P, R.s_c1, ex, o, o_near);
+    }
+    const Best best = ex.best;
+    if (best.ij == 0xFFFFFFFFu || !(best.p < 1.0)) {
+        // no cell beats the cells the reference short-circuits to p = 1.0: needs the dense path
+        if (lane == 0) status[task] = 2;
+        __syncwarp();
+        return;
+    }
+    if (lane == 0) {
+        const uint32_t bi = best.ij >> 16, bj = best.ij & 0xFFFFu;
+        dto_b200_record r;
+        r.rank1 = P.thr1[bi];
+        r.rank2 = P.thr2[bj];
+        r.set1_len = R.s_c1[bi];
+        r.set2_len = P.c2[bj];
+        r.intersection_size = best.k;
+        r.flags = record_flags | (ex.near ? DTO_B200_FLAG_NEAR_TIE : 0u);
+        r.population_size = P.N;
+        r.pvalue = best.p;
+        out[task] = r;
+        status[task] = 0;
+    }
+    // per-lane counters -> one atomic per warp
+    uint32_t ne = R.n_eval, nr = R.n_refine;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ne += __shfl_xor_sync(kFull, ne, off);
+        nr += __shfl_xor_sync(kFull, nr, off);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[0], (unsigned long long)ne);
+        atomicAdd(&counters[1], (unsigned long long)R.n_level2);
+        atomicAdd(&counters[2], (unsigned long long)nr);
+        if (task_stats) {
+            uint32_t *ts = task_stats + (size_t)kTaskStatWords * task;
+            ts[0] = R.n_level2;
+            ts[1] = nr;
+            ts[2] = ne;
+            ts[3] = (uint32_t)((clock64() - t_begin) >> 4);
+            ts[4] = (uint32_t)level;
+            ts[5] = ts[6] = ts[7] = 0;
+        }
+    }
+    __syncwarp();
+}
+
 template <int CH>
-__global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : 2)
-scan_kernel(const Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
+__global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : kScanCtasPerSm)
+scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
             dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
             unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats) {
     using L = ScanLayout<CH>;
     constexpr int CHP = L::CHP;
-    constexpr uint32_t cap = (uint32_t)L::CAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *s_c1 = reinterpret_cast<uint32_t *>(smem_raw);  // [T1] shared by the CTA
@@ -425,206 +656,59 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint3
     unsigned char *wbase = smem_raw + c1_bytes + (size_t)warp * L::per_warp;
     uint32_t *D = reinterpret_cast<uint32_t *>(wbase);
     uint32_t *Qij = reinterpret_cast<uint32_t *>(wbase + L::d_bytes);
-    uint32_t *Qk = Qij + L::QCAP;
-    uint32_t *qcnt = Qk + L::QCAP;
+    uint16_t *Qk = reinterpret_cast<uint16_t *>(Qij + L::QCAP);
+    uint32_t *qcnt = reinterpret_cast<uint32_t *>(wbase + L::d_bytes + L::q_bytes);
     Cand *cand = reinterpret_cast<Cand *>(wbase + L::d_bytes + L::q_bytes + 16);
     uint16_t *ring = reinterpret_cast<uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
-    const unsigned lt = (1u << lane) - 1u;
 
     for (int x = threadIdx.x; x < P.T1; x += blockDim.x) s_c1[x] = P.c1[x];
     __syncthreads();
 
-    // dynamic scheduling: permutations differ in cost (the occasional one has a wide blob of near-minimal cells)
+    // dynamic scheduling: permutations differ in cost (how many cells pass the screen)
     for (;;) {
         int task = 0;
         if (lane == 0) task = (int)atomicAdd(reinterpret_cast<unsigned int *>(&counters[7]), 1u);
         task = __shfl_sync(kFull, task, 0);
         if (task >= n_tasks) break;
         const uint16_t *__restrict__ row = pb + (size_t)task * P.pb_stride;
-        const long long t_begin = clock64();
+        const long long t_begin = task_stats ? clock64() : 0;
         for (int x = lane; x < 32 * CHP; x += 32) D[x] = 0;
         if (lane == 0) *qcnt = 0;
         __syncwarp();
+
+        Rare R;
+        R.theta = CUDART_INF;
+        R.ex.best.p = CUDART_INF;
+        R.ex.best.k = 0;
+        R.ex.best.ij = 0xFFFFFFFFu;
+        R.ex.near = false;
+        R.zero.p = 0.0;
+        R.zero.k = 0;
+        R.zero.ij = 0xFFFFFFFFu;
+        R.ncand = 0;
+        R.n_level2 = R.n_eval = R.n_refine = 0;
+        R.s_c1 = s_c1;
+        R.Qij = Qij;
+        R.Qk = Qk;
+        R.qcnt = qcnt;
+        R.cand = cand;
+        R.lane = lane;
 
         uint32_t kcur[CH];
 #pragma unroll
         for (int m = 0; m < CH; ++m) kcur[m] = 0;
         uint32_t koff = 0;
-        double theta = CUDART_INF;  // certified: log(min p of the reference) <= theta
         int level = 0;
-        uint32_t ncand = 0;
-        Exact ex;  // per-lane running optimum over everything evaluated exactly so far
-        ex.best.p = CUDART_INF;
-        ex.best.k = 0;
-        ex.best.ij = 0xFFFFFFFFu;
-        ex.near = false;
-        Best zero;  // best cell on the underflow plateau (reference p == 0.0)
-        zero.p = 0.0;
-        zero.k = 0;
-        zero.ij = 0xFFFFFFFFu;
-        unsigned long long n_level2 = 0, n_eval = 0, n_refine = 0;
-        long long tm_drain = 0, tm_refine = 0, tm_eval = 0, tm_scatter = 0, tm_compact = 0, n_drain_iter = 0;
-        const bool timing = task_stats != nullptr;
 
-        // (3b) refine: tail by the ratio recurrence (no exp, no table walk) -> log p to ~1e-10 for every buffered
-        //      candidate not refined yet; tightens theta so that only cells within 1e-8 of the minimum survive
-        auto refine_buffer = [&]() {
-            const long long t0 = timing ? clock64() : 0;
-            double th = CUDART_INF;
-            for (uint32_t idx = lane; idx < ncand; idx += 32) {
-                Cand c = cand[idx];
-                if (c.k & kRefinedBit) continue;
-                const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
-                const uint32_t K = s_c1[i], n = P.c2[j], k = c.k;
-                const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
-                double a = (double)(K - k), b = (double)(n - k);
-                double cc = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
-                double t = 1.0, S = 1.0;
-                // pmf(k+1)/pmf(k) = a b / (cc d); then a, b fall and cc, d rise by one per step
-                while (a > 0.0 && b > 0.0) {
-                    t *= (a * b) / (cc * d);
-                    S += t;
-                    if (t < S * 0x1p-53 && (a * b) < (cc * d)) break;
-                    a -= 1.0;
-                    b -= 1.0;
-                    cc += 1.0;
-                    d += 1.0;
-                }
-                const double lp = s + log(S);
-                if (task == P.debug_task && n_refine < 4000 && (n_refine % 40) == 0)
-                    printf("refine i=%u j=%u K=%u n=%u k=%u level=%d theta=%.4f s=%.4f lp=%.4f oldv=%.4f meta=(%u,%u,%u)\n", i, j, K, n, k, level, theta, s, lp, c.v,
-                           P.cellmeta[(size_t)i * P.T2 + j].x, P.cellmeta[(size_t)i * P.T2 + j].y & 0xFFFFu, P.cellmeta[(size_t)i * P.T2 + j].y >> 16);
-                c.v = lp - kRefineEps + kEps;
-                c.k |= kRefinedBit;
-                cand[idx] = c;
-                th = fmin(th, lp + kRefineEps);
-                ++n_refine;
-            }
-            theta = fmin(theta, warp_min(th));
-            __syncwarp();
-            if (timing) tm_refine += clock64() - t0;
-        };
-
-        // (4) statrs-order FP64 tail for every buffered candidate, one per lane; empties the buffer and
-        //     tightens theta to the exact minimum seen so far
-        auto evaluate_buffer = [&]() {
-            const long long t0 = timing ? clock64() : 0;
-            double th = CUDART_INF;
-            for (uint32_t idx = lane; idx < ncand; idx += 32) {
-                const Cand c = cand[idx];
-                const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
-                Best b;
-                b.k = c.k & ~kRefinedBit;
-                b.p = hypergeom_pvalue_exact(P.lf, P.N, s_c1[i], P.c2[j], b.k);
-                b.ij = c.ij;
-                merge_exact(P, s_c1, ex, b, false);
-                th = fmin(th, b.p > 0.0 ? log(b.p) + kEps : kZeroHi);
-            }
-            n_eval += ncand;
-            theta = fmin(theta, warp_min(th));
-            ncand = 0;
-            __syncwarp();
-            if (timing) tm_eval += clock64() - t0;
-        };
-
-        // drains the queue of cells that passed the critical-overlap screen, 32 at a time
-        auto drain = [&](bool flush) {
-            const long long t0 = timing ? clock64() : 0;
-            uint32_t qc = *qcnt;
-            while (qc >= 32 || (flush && qc > 0)) {
-                const uint32_t take = qc < 32 ? qc : 32;
-                const uint32_t start = qc - take;
-                const bool valid = (uint32_t)lane < take;
-                Cand e;
-                e.ij = 0;
-                e.k = 0;
-                e.v = CUDART_INF;
-                double ub = CUDART_INF;
-                bool keep = false;
-                if (valid) {
-                    e.ij = Qij[start + lane];
-                    e.k = Qk[start + lane];
-                    const uint32_t i = e.ij >> 16, j = e.ij & 0xFFFFu;
-                    const uint32_t K = s_c1[i], n = P.c2[j], k = e.k;
-                    const uint2 meta = P.cellmeta[(size_t)i * P.T2 + j];
-                    const uint32_t dk = k - (meta.y & 0xFFFFu);
-                    if (dk < (meta.y >> 16)) {
-                        // tabulated: log p of this (cell, k) to ~1e-10, no arithmetic at all
-                        const double lp = P.lptab[meta.x + dk];
-                        ub = lp + kRefineEps - kEps;
-                        e.v = lp - kRefineEps + kEps;
-                        e.k |= kRefinedBit;
-                        keep = true;
-                    } else if (k < (meta.y & 0xFFFFu)) {
-                        // below the tabulated range: the table build certified p(kbase - 1) > tau_1, and p falls with k
-                        e.v = P.level_log[1];
-                        keep = true;
-                    } else {
-                        const double s = log_pmf(P, P.rowA[i], P.colB[j], K, n, k);
-                        const double a = (double)(K - k), b = (double)(n - k);
-                        const double c = (double)k + 1.0, d = (double)(P.N - K - n + k) + 1.0;
-                        const double r1 = (a * b) / (c * d);  // pmf(k+1) / pmf(k)
-                        if (r1 < 1.0 && s < kZeroLo) {
-                            // every tail term underflows: the reference's p is exactly 0.0 -> integer tie-break only
-                            Best z;
-                            z.p = 0.0;
-                            z.k = k;
-                            z.ij = e.ij;
-                            if (better(z, zero)) zero = z;
-                            ub = kZeroHi - kEps;
-                        } else {
-                            double lb = s;  // p >= pmf(k)
-                            if (r1 < 1.0) {
-                                ub = s - log1p(-r1);  // ratios fall with k: p <= pmf(k) / (1 - r1)
-                                // ratios over the next mm steps are all >= r_mm: p >= pmf * (1 - r^(mm+1)) / (1 - r)
-                                double mm = floor(2.0 / (1.0 - r1)) + 1.0;
-                                mm = fmin(mm, fmin(a, b));
-                                if (mm >= 1.0) {
-                                    const double rm = ((a - mm + 1.0) * (b - mm + 1.0)) / ((c + mm - 1.0) * (d + mm - 1.0));
-                                    if (rm > 0.0 && rm < 1.0) lb = s + log((1.0 - exp((mm + 1.0) * log(rm))) / (1.0 - rm));
-                                }
-                            }
-                            e.v = lb;
-                            keep = true;
-                        }
-                    }
-                }
-                theta = fmin(theta, warp_min(ub + kEps));
-                keep = keep && (e.v - kEps <= theta);
-                const unsigned bal = __ballot_sync(kFull, keep);
-                const uint32_t add = __popc(bal);
-                if (ncand + add > cap) {
-                    ncand = compact_cands(cand, ncand, theta, lane);
-                    if (ncand + add > cap) {  // still full: sharpen the survivors' bounds, then drop the beaten ones
-                        refine_buffer();
-                        ncand = compact_cands(cand, ncand, theta, lane);
-                    }
-                    if (ncand + add > cap) evaluate_buffer();  // genuinely full of near-ties: settle them exactly
-                    keep = keep && (e.v - kEps <= theta);
-                }
-                const unsigned bal2 = __ballot_sync(kFull, keep);
-                if (keep) cand[ncand + __popc(bal2 & lt)] = e;
-                ncand += __popc(bal2);
-                __syncwarp();
-                n_level2 += take;
-                ++n_drain_iter;
-                qc = start;
-            }
-            if (lane == 0) *qcnt = qc;
-            __syncwarp();
-            while (level < P.levels && theta <= P.level_log[level + 1]) ++level;
-            if (timing) tm_drain += clock64() - t0;
-        };
-
-        // partner-slot row staged through shared memory with cp.async: chunk c = positions [256c, 256c+256), one 16 B
-        // copy per lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)
-        const uint32_t n_chunks = P.pb_stride >> 8;
+        // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
+        // lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)
+        const uint32_t n_chunks = P.pb_stride / kChunk;
         auto issue_chunk = [&](uint32_t c) {
             if (c < n_chunks) {
-                const uint16_t *src = row + ((size_t)c << 8) + lane * 8;
-                const uint32_t dst = ring_addr + (((c & 3u) << 8) + lane * 8) * 2;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                const uint16_t *src = row + (size_t)c * kChunk + lane * 4;
+                const uint32_t dst = ring_addr + ((c & 3u) * kChunk + lane * 4) * 2;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -642,9 +726,8 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint3
 #pragma unroll
             for (int m = 0; m < CH; ++m) kc[m] = __ldg(kr + m * 32);
             // (1) bin this row's genes: position -> partner's column slot, privatised per warp
-            const long long ts0 = timing ? clock64() : 0;
             while (lo < hi) {
-                if ((lo >> 8) > cbase) {  // chunk cbase is consumed: cbase+2 must have landed, refill its slot
+                if ((lo / kChunk) > cbase) {  // chunk cbase is consumed: cbase+2 must have landed, refill its slot
                     ++cbase;
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
@@ -660,7 +743,6 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint3
                 lo = e;
             }
             __syncwarp();
-            if (timing) tm_scatter += clock64() - ts0;
             // (2) 2-D inclusive prefix: lane-local run over its CH columns + warp exclusive scan of lane totals
             uint32_t run = 0;
 #pragma unroll
@@ -677,73 +759,32 @@ scan_kernel(const Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint3
                 if (lane >= o) inc += v;
             }
             koff += inc - run;
-            // (3) screen: only k >= kcrit can have p <= tau_level
+            // (3) screen: only k >= kcrit can have p <= tau_level.  Two halves so the queue only needs half a row.
 #pragma unroll
-            for (int m = 0; m < CH; ++m) {
+            for (int m = 0; m < L::HALF; ++m) {
                 const uint32_t k = kcur[m] + koff;
                 if (k >= kc[m]) {
                     const uint32_t slot = atomicAdd(qcnt, 1u);
                     Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + m);
-                    Qk[slot] = k;
+                    Qk[slot] = (uint16_t)k;
                 }
             }
             __syncwarp();
-            if (*qcnt >= 32) drain(false);
-        }
-
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        drain(true);
-        ncand = compact_cands(cand, ncand, theta, lane);
-        refine_buffer();
-        ncand = compact_cands(cand, ncand, theta, lane);
-        evaluate_buffer();
-        merge_exact(P, s_c1, ex, zero, false);
-        // (5) warp-shuffle argmin with the reference tie-break
+            if (*qcnt >= 32) level = drain_queue(P, R, false, level);
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            Best o;
-            o.p = __shfl_xor_sync(kFull, ex.best.p, off);
-            o.k = __shfl_xor_sync(kFull, ex.best.k, off);
-            o.ij = __shfl_xor_sync(kFull, ex.best.ij, off);
-            const bool o_near = __shfl_xor_sync(kFull, (int)ex.near, off) != 0;
-            merge_exact(P, s_c1, ex, o, o_near);
-        }
-        const Best best = ex.best;
-        if (best.ij == 0xFFFFFFFFu || !(best.p < 1.0)) {
-            // no cell beats the cells the reference short-circuits to p = 1.0: needs the dense path
-            if (lane == 0) status[task] = 2;
-            __syncwarp();
-            continue;
-        }
-        if (lane == 0) {
-            const uint32_t bi = best.ij >> 16, bj = best.ij & 0xFFFFu;
-            dto_b200_record r;
-            r.rank1 = P.thr1[bi];
-            r.rank2 = P.thr2[bj];
-            r.set1_len = s_c1[bi];
-            r.set2_len = P.c2[bj];
-            r.intersection_size = best.k;
-            r.flags = record_flags | (ex.near ? DTO_B200_FLAG_NEAR_TIE : 0u);
-            r.population_size = P.N;
-            r.pvalue = best.p;
-            out[task] = r;
-            status[task] = 0;
-            atomicAdd(&counters[0], n_eval);
-            atomicAdd(&counters[1], n_level2);
-            atomicAdd(&counters[2], n_refine);
-            if (task_stats) {
-                uint32_t *ts = task_stats + (size_t)kTaskStatWords * task;
-                ts[0] = (uint32_t)n_level2;
-                ts[1] = (uint32_t)n_refine;
-                ts[2] = (uint32_t)n_eval;
-                ts[3] = (uint32_t)((clock64() - t_begin) >> 4);
-                ts[4] = (uint32_t)(tm_scatter >> 4);
-                ts[5] = (uint32_t)(tm_drain >> 4);
-                ts[6] = (uint32_t)(tm_refine >> 4);
-                ts[7] = (uint32_t)(tm_eval >> 4);
+            for (int m = L::HALF; m < CH; ++m) {
+                const uint32_t k = kcur[m] + koff;
+                if (k >= kc[m]) {
+                    const uint32_t slot = atomicAdd(qcnt, 1u);
+                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + m);
+                    Qk[slot] = (uint16_t)k;
+                }
             }
+            __syncwarp();
+            if (*qcnt >= 32) level = drain_queue(P, R, false, level);
         }
-        __syncwarp();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        finish_task(P, R, task, level, record_flags, out, status, counters, task_stats, t_begin);
     }
 }
 
@@ -875,7 +916,7 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
 size_t scan_smem_bytes(int CH, int T1, int warps) {
     const size_t chp = (size_t)(CH | 1);
     const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
-    const size_t q = (size_t)(32 * CH + 32) * 8;
+    const size_t q = ((size_t)(32 * ((CH + 1) / 2) + 64) * 6 + 15) & ~(size_t)15;
     const size_t per = d + q + 16 + (size_t)kCandCap * sizeof(Cand) + (size_t)kRing * 2;
     return (((size_t)T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * per;
 }

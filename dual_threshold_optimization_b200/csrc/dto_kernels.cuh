@@ -6,10 +6,12 @@
 namespace dto {
 
 constexpr int kScanThreads = 256;   // max threads per CTA of the scan kernel (8 warps = 8 permutations)
+constexpr int kScanCtasPerSm = 3;   // occupancy the scan kernel is compiled for (registers <= 65536 / (256 * 3))
 constexpr int kSigmaThreads = 1024; // one CTA per permutation in the pairing kernel
-constexpr int kCandCap = 256;       // per-warp shared-memory candidate buffer (entries)
+constexpr int kCandCap = 64;        // per-warp shared-memory candidate buffer (entries)
 constexpr int kTaskStatWords = 8;   // per-task diagnostics words (option task_stats)
-constexpr int kRing = 1024;         // per-warp staging ring of partner slots (u16), 4 cp.async chunks of 256
+constexpr int kChunk = 128;         // positions per cp.async chunk (8 B per lane)
+constexpr int kRing = 4 * kChunk;   // per-warp staging ring of partner slots (u16)
 
 int pick_ch(int T2);
 int pick_bucket_bits(uint32_t n);
