@@ -98,7 +98,7 @@ struct dto_b200_ctx {
     DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts;
     // batch state
     DevBuf d_pb, d_records, d_status, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
-        d_err, d_pair, d_minp, d_tstats;
+        d_err, d_pair, d_minp, d_tstats, d_words;
     bool opt_task_stats = false;
     int opt_debug_task = -1;
     int last_batch_n = 0;
@@ -265,7 +265,7 @@ void dto_b200_destroy(dto_b200_ctx *ctx) {
                       &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
                       &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_H,
                       &ctx->d_pv, &ctx->d_logp, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_err, &ctx->d_pair,
-                      &ctx->d_minp, &ctx->d_tstats};
+                      &ctx->d_minp, &ctx->d_tstats, &ctx->d_words};
     for (DevBuf *b : bufs) b->release();
     ctx->h_records.release();
     ctx->h_status.release();
@@ -534,10 +534,17 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
     if (Pn == 0) return DTO_B200_OK;
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    if (sigma_smem_bytes(P, B1, B2) > ctx->smem_optin)
-        return fail(DTO_B200_ERR_UNSUPPORTED,
-                    "pairing kernel needs %zu B of shared memory (> %zu): lists this long are not supported yet",
-                    sigma_smem_bytes(P, B1, B2), ctx->smem_optin);
+    // lists too long for the in-shared-memory sort buffer keep it in a per-CTA global scratch (L2-resident)
+    const bool words_in_smem = sigma_smem_bytes(P, B1, B2, true) <= ctx->smem_optin;
+    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
+        return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel needs %zu B of shared memory (> %zu)",
+                    sigma_smem_bytes(P, B1, B2, false), ctx->smem_optin);
+    const int sigma_grid_max = ctx->sm_count * (words_in_smem ? 4 : 1);
+    uint32_t *words_scratch = nullptr;
+    if (!words_in_smem) {
+        CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * std::max(P.n1, P.n2) * 4));
+        words_scratch = ctx->d_words.as<uint32_t>();
+    }
     const size_t batch = (size_t)auto_batch(ctx);
     ctx->stats.last_scan_kernel_ms = 0;
     ctx->stats.last_sigma_kernel_ms = 0;
@@ -558,8 +565,8 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
         const int n = (int)std::min(batch, Pn - done);
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
         CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
-        CUDA_TRY(launch_sigma_sort(P, seed, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr,
-                                   std::min(n, ctx->sm_count * 4), ctx->stream));
+        CUDA_TRY(launch_sigma_sort(P, seed, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr, words_scratch,
+                                   std::min(n, sigma_grid_max), ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
         ctx->stats.kernel_launches += 1;
         rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
@@ -608,12 +615,18 @@ int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, 
     if (!pos2_of_pos1_out) return fail(DTO_B200_ERR_INVALID, "null output");
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    if (sigma_smem_bytes(P, B1, B2) > ctx->smem_optin)
+    const bool words_in_smem = sigma_smem_bytes(P, B1, B2, true) <= ctx->smem_optin;
+    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel does not fit shared memory");
+    uint32_t *words_scratch = nullptr;
+    if (!words_in_smem) {
+        CUDA_TRY(ctx->d_words.ensure((size_t)std::max(P.n1, P.n2) * 4));
+        words_scratch = ctx->d_words.as<uint32_t>();
+    }
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
     CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_pair.p, 0xFF, (size_t)(P.n1 ? P.n1 : 1) * 4, ctx->stream));
-    CUDA_TRY(launch_sigma_sort(P, seed, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), 1, ctx->stream));
+    CUDA_TRY(launch_sigma_sort(P, seed, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), words_scratch, 1, ctx->stream));
     ctx->stats.kernel_launches += 1;
     CUDA_TRY(cudaMemcpyAsync(pos2_of_pos1_out, ctx->d_pair.p, (size_t)P.n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -124,14 +124,16 @@ __global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ 
 
 // =====================================================================================================
 // K0: exactly-uniform random pairing by sorting Philox keys in shared memory.
-//   key(e) = 32 random bits; elements are bucketed by the top B bits (histogram + exclusive scan + scatter with
-//   shared-memory atomics), then ranked inside their bucket (~8 members) on (next 16 key bits, secondary Philox
-//   key on ties, index) -- a total order, so the result does not depend on the order atomics resolve in.
+//   key(e) = 32 random bits.  Pass 1: bucket = top B bits (B ~ log2 n - 1, ~1.2 elements per bucket); ONE shared-
+//   memory atomic per element both counts the bucket and hands the element its arrival slot.  Pass 2: exclusive
+//   scan of the counts.  Pass 3: element -> words[off[bucket] + arrival] = (next 16 key bits << 16 | element).
+//   Pass 4: every element ranks itself inside its bucket on (16 key bits, secondary Philox key on a tie, index) --
+//   a total order, so the result does not depend on the order the atomics resolved in.
 // =====================================================================================================
 struct SortShared {
-    uint32_t *words;   // [n]     (rem16 << 16) | element
-    uint32_t *off;     // [NB+1]  bucket offsets (exclusive scan of the histogram)
-    uint32_t *cursor;  // [NB]
+    uint32_t *words;     // [n]     (rem16 << 16) | element, bucket-contiguous
+    uint32_t *cnt;       // [NB+1]  bucket counts, then offsets (exclusive scan)
+    uint16_t *arrival;   // [n]     arrival slot inside the bucket (aliases the staged output row)
     uint32_t *scan_tmp;  // [32]
 };
 
@@ -150,14 +152,27 @@ __device__ __forceinline__ uint32_t secondary_key(uint64_t seed, uint64_t perm_i
     return c[e & 3u];
 }
 
-// exclusive scan of a[0..len) in place, a[len] = total; blockDim.x threads
+// exclusive scan of a[0..len) in place, a[len] = total; blockDim.x threads.  When len is a multiple of 4 * blockDim.x
+// every thread owns a contiguous run held in registers (128-bit shared loads/stores); otherwise a plain serial run.
 __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t per = (len + nt - 1) / nt;
-    const uint32_t b = tid * per, e = (b + per < len) ? b + per : len;
-    uint32_t sum = 0;
-    for (uint32_t x = b; x < e; ++x) sum += a[x];
     const uint32_t lane = tid & 31, w = tid >> 5;
+    const bool vec = (len % (4 * nt)) == 0 && len / nt <= 16;
+    const uint32_t per = vec ? len / nt : (len + nt - 1) / nt;
+    const uint32_t b = tid * per, e = (b + per < len) ? b + per : len;
+    uint4 r[4];
+    uint32_t sum = 0;
+    if (vec) {
+        const uint4 *a4 = reinterpret_cast<const uint4 *>(a + b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((uint32_t)q * 4 < per) {
+                r[q] = a4[q];
+                sum += r[q].x + r[q].y + r[q].z + r[q].w;
+            }
+    } else {
+        for (uint32_t x = b; x < e; ++x) sum += a[x];
+    }
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -177,13 +192,47 @@ __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     }
     __syncthreads();
     uint32_t run = tmp[w] + inc - sum;
-    for (uint32_t x = b; x < e; ++x) {
-        const uint32_t v = a[x];
-        a[x] = run;
-        run += v;
+    if (vec) {
+        uint4 *a4 = reinterpret_cast<uint4 *>(a + b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if ((uint32_t)q * 4 < per) {
+                uint4 o;
+                o.x = run;
+                o.y = o.x + r[q].x;
+                o.z = o.y + r[q].y;
+                o.w = o.z + r[q].z;
+                run = o.w + r[q].w;
+                a4[q] = o;
+            }
+    } else {
+        for (uint32_t x = b; x < e; ++x) {
+            const uint32_t v = a[x];
+            a[x] = run;
+            run += v;
+        }
     }
-    if (tid == nt - 1) a[len] = run;  // the last thread's chunk ends at len (or is empty): run == total
+    if (tid == nt - 1) a[len] = run;  // the last thread's run ends at len (or is empty): run == total
     __syncthreads();
+}
+
+// 16-bit tie inside a bucket: fresh random bits (a second Philox stream) decide, then the index.  Kept out of line
+// so the common path carries no Philox evaluation.
+__device__ __noinline__ uint32_t rank_with_ties(const uint32_t *words, uint32_t lo, uint32_t hi, uint32_t e, uint32_t rem,
+                                                uint64_t seed, uint64_t perm_id, uint32_t stream) {
+    const uint32_t sec = secondary_key(seed, perm_id, stream, e);
+    uint32_t rank = 0;
+    for (uint32_t y = lo; y < hi; ++y) {
+        const uint32_t v = words[y];
+        const uint32_t ve = v & 0xFFFFu;
+        if ((v >> 16) < rem) {
+            ++rank;
+        } else if ((v >> 16) == rem && ve != e) {
+            const uint32_t os = secondary_key(seed, perm_id, stream, ve);
+            if (os < sec || (os == sec && ve < e)) ++rank;
+        }
+    }
+    return rank;
 }
 
 // Ranks the n elements of one Philox stream; calls emit(e, f): element e has the f-th smallest key.
@@ -192,7 +241,7 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
                                           uint32_t stream, Emit emit) {
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    for (uint32_t x = tid; x <= NB; x += nt) S.off[x] = 0;
+    for (uint32_t x = tid; x <= NB; x += nt) S.cnt[x] = 0;
     __syncthreads();
     const uint32_t nblk = (n + 3) >> 2;
     for (uint32_t c = tid; c < nblk; c += nt) {
@@ -201,13 +250,11 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t e = c * 4 + q;
-            if (e < n) atomicAdd(&S.off[key[q] >> (32 - B)], 1u);
+            if (e < n) S.arrival[e] = (uint16_t)atomicAdd(&S.cnt[key[q] >> (32 - B)], 1u);
         }
     }
     __syncthreads();
-    block_exclusive_scan(S.off, NB, S.scan_tmp);
-    for (uint32_t x = tid; x < NB; x += nt) S.cursor[x] = S.off[x];
-    __syncthreads();
+    block_exclusive_scan(S.cnt, NB, S.scan_tmp);
     for (uint32_t c = tid; c < nblk; c += nt) {
         uint32_t key[4];
         philox_keys(key, seed, perm_id, stream, c);
@@ -215,12 +262,13 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
         for (int q = 0; q < 4; ++q) {
             const uint32_t e = c * 4 + q;
             if (e < n) {
-                const uint32_t pos = atomicAdd(&S.cursor[key[q] >> (32 - B)], 1u);
+                const uint32_t pos = S.cnt[key[q] >> (32 - B)] + S.arrival[e];
                 S.words[pos] = (((key[q] >> (16 - B)) & 0xFFFFu) << 16) | e;
             }
         }
     }
     __syncthreads();
+    // pass 4, per element again (buckets hold ~1.2 members, so the scan of one's own bucket is 1-3 loads)
     for (uint32_t c = tid; c < nblk; c += nt) {
         uint32_t key[4];
         philox_keys(key, seed, perm_id, stream, c);
@@ -230,24 +278,15 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
             if (e < n) {
                 const uint32_t b = key[q] >> (32 - B);
                 const uint32_t rem = (key[q] >> (16 - B)) & 0xFFFFu;
-                const uint32_t lo = S.off[b], hi = S.off[b + 1];
+                const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
                 uint32_t rank = 0;
-                uint32_t sec = 0;
-                bool have_sec = false;
-                for (uint32_t x = lo; x < hi; ++x) {
-                    const uint32_t w = S.words[x];
-                    const uint32_t wr = w >> 16, we = w & 0xFFFFu;
-                    if (wr < rem) {
-                        ++rank;
-                    } else if (wr == rem && we != e) {  // 16-bit tie inside the bucket: decide on fresh random bits
-                        if (!have_sec) {
-                            sec = secondary_key(seed, perm_id, stream, e);
-                            have_sec = true;
-                        }
-                        const uint32_t os = secondary_key(seed, perm_id, stream, we);
-                        if (os < sec || (os == sec && we < e)) ++rank;
-                    }
+                bool tie = false;
+                for (uint32_t y = lo; y < hi; ++y) {
+                    const uint32_t v = S.words[y];
+                    rank += ((v >> 16) < rem) ? 1u : 0u;
+                    tie = tie || ((v >> 16) == rem && (v & 0xFFFFu) != e);
                 }
+                if (tie) rank = rank_with_ties(S.words, lo, hi, e, rem, seed, perm_id, stream);  // ~2^-16 per pair
                 emit(e, lo + rank);
             }
         }
@@ -255,48 +294,58 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const Problem P, uint64_t seed, uint64_t first_id,
-                                                                   int n_tasks, int B1, int B2,
+__global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed,
+                                                                   uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
-                                                                   uint32_t *__restrict__ pairing_out) {
+                                                                   uint32_t *__restrict__ pairing_out,
+                                                                   uint32_t *__restrict__ words_scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
+    // layout: cnt[NB+1] | scan_tmp[33] | stage[max(pb_stride, nmax)] u16 | order2[n_common] u16 | words[nmax] u32 (or global)
     SortShared S;
-    S.words = reinterpret_cast<uint32_t *>(smem_raw);
-    S.off = S.words + nmax;
-    S.cursor = S.off + (1u << Bmax) + 1;
-    S.scan_tmp = S.cursor + (1u << Bmax);
-    uint16_t *out = reinterpret_cast<uint16_t *>(S.scan_tmp + 32);  // [pb_stride]
-    uint16_t *order2 = out + P.pb_stride;                           // [n_common] (general mode only)
+    S.cnt = reinterpret_cast<uint32_t *>(smem_raw);
+    S.scan_tmp = S.cnt + (1u << Bmax) + 1;
+    const uint32_t stage_len = P.pb_stride > nmax ? P.pb_stride : nmax;
+    uint16_t *stage = reinterpret_cast<uint16_t *>(S.scan_tmp + 33);  // (NB + 1 + 33) words: 8-byte aligned for B >= 1
+    S.arrival = stage;  // dead before the staged output row is written
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
+    uint16_t *order2 = stage + ((stage_len + 1) & ~1u);
+    uint16_t *after = order2 + (identical ? 0u : ((P.n_common + 1) & ~1u));
+    S.words = words_scratch ? words_scratch + (size_t)blockIdx.x * nmax
+                            : reinterpret_cast<uint32_t *>(after + ((4 - ((uintptr_t)after & 3)) & 3) / 2);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
 
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const uint64_t perm_id = first_id + (uint64_t)t;
-        for (uint32_t x = tid; x < P.pb_stride; x += nt) out[x] = kNoSlot;
-        __syncthreads();
+        uint16_t *dst = pb + (size_t)t * P.pb_stride;
         if (identical) {
-            // element = list-2 position e, rank f = the list-1 position it is paired with
+            // element = list-2 position e, rank f = the list-1 position it is paired with.  The emit of pass 4 must not
+            // overwrite `arrival` (aliased with the staging row) -- pass 3 has consumed it by then.
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
-                if (f < P.n1_eff) out[f] = P.dslot2[e];
+                if (f < P.n1_eff) stage[f] = P.dslot2[e];
                 if (pairing_out) pairing_out[(size_t)t * P.n1 + f] = e;
             });
+            for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
         } else {
             // uniform random partial injection: the n_common lowest-keyed positions of each list, matched by rank
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 1u, [&](uint32_t e, uint32_t f) {
                 if (f < P.n_common) order2[f] = (uint16_t)e;
             });
+            // the second sort's emit writes stage[e] for every list-1 position e < n1_eff
             block_rank_by_random_keys(S, P.n1, B1, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
                 uint32_t partner = 0xFFFFFFFFu;
                 if (f < P.n_common) partner = order2[f];
-                if (e < P.n1_eff && partner != 0xFFFFFFFFu) out[e] = P.dslot2[partner];
+                if (e < P.n1_eff) stage[e] = partner != 0xFFFFFFFFu ? P.dslot2[partner] : kNoSlot;
                 if (pairing_out) pairing_out[(size_t)t * P.n1 + e] = partner;
             });
+            for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
         }
         __syncthreads();
-        uint16_t *dst = pb + (size_t)t * P.pb_stride;
-        for (uint32_t x = tid; x < P.pb_stride; x += nt) dst[x] = out[x];
+        // coalesced copy-out, 8 bytes per thread (pb_stride is a multiple of 256, rows are 512 B aligned)
+        const uint2 *s2 = reinterpret_cast<const uint2 *>(stage);
+        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
+        for (uint32_t x = tid; x < P.pb_stride / 4; x += nt) d2[x] = s2[x];
         __syncthreads();
     }
 }
@@ -962,32 +1011,36 @@ cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *
     return cudaGetLastError();
 }
 
-size_t sigma_smem_bytes(const Problem &P, int B1, int B2) {
+// shared-memory bytes of the pairing kernel; words_in_smem = false moves the n x 4 B sort buffer to a global scratch
+size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem) {
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
-    size_t b = (size_t)nmax * 4 + ((size_t)(1u << Bmax) * 2 + 1 + 32) * 4;
-    b += (size_t)P.pb_stride * 2;
+    const uint32_t stage_len = P.pb_stride > nmax ? P.pb_stride : nmax;
+    size_t b = ((size_t)(1u << Bmax) + 1 + 33) * 4;
+    b += (size_t)((stage_len + 1) & ~1u) * 2;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
-    if (!identical) b += (size_t)P.n_common * 2 + 2;
+    if (!identical) b += (size_t)((P.n_common + 1) & ~1u) * 2;
+    b += 4;
+    if (words_in_smem) b += (size_t)nmax * 4;
     return (b + 15) & ~(size_t)15;
 }
 
 int pick_bucket_bits(uint32_t n) {
     int lg = 0;
     while ((1ull << lg) < n) ++lg;
-    int B = lg - 3;
+    int B = lg - 1;  // 1..2 elements per bucket
     if (B < 1) B = 1;
-    if (B > 13) B = 13;
+    if (B > 14) B = 14;
     return B;
 }
 
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
-                              uint32_t *pairing_out, int grid, cudaStream_t st) {
+                              uint32_t *pairing_out, uint32_t *words_scratch, int grid, cudaStream_t st) {
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    const size_t smem = sigma_smem_bytes(P, B1, B2);
+    const size_t smem = sigma_smem_bytes(P, B1, B2, words_scratch == nullptr);
     cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out);
+    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, words_scratch);
     return cudaGetLastError();
 }
 
