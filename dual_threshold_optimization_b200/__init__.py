@@ -6,7 +6,7 @@ from .collections import Feature, FeatureList, PermutedRankedFeatureList, Ranked
 from .dto import OptimizationResultRecord, compute_population_size, optimize, process_threshold_pairs  # noqa: F401
 from .engine import Engine, device_count  # noqa: F401
 from .read import read_feature_list_from_file, read_ranked_feature_list_from_csv  # noqa: F401
-from .run import Task, run_multi_gpu, run_single_node  # noqa: F401
+from .run import Task, run_multi_gpu, run_pairs, run_single_node  # noqa: F401
 from .stat_operations import empirical_pvalue, fdr, hypergeometric_pvalue, intersect_genes  # noqa: F401
 
 __version__ = "0.1.0"

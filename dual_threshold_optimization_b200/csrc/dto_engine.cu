@@ -481,8 +481,18 @@ int dto_b200_run_unpermuted(dto_b200_ctx *ctx, dto_b200_record *record_out) {
     ctx->stats.last_scan_kernel_ms = 0;
     ctx->stats.last_sigma_kernel_ms = 0;
     ctx->stats.last_scan_launches = 0;
-    rc = run_tasks(ctx, 1, 0u);
-    if (rc) return rc;
+    // One task cannot fill the GPU through the warp-per-permutation scan, and for strongly concordant lists nearly
+    // every cell is deep in the tail; the dense grid (every cell evaluated in statrs order on all SMs) is both exact
+    // and fast here: optimize(l1, l2, permute = false, ..) == argmin of the debug grid (optimize_main.rs:73-116).
+    const size_t cells = (size_t)P.T1 * P.T2;
+    CUDA_TRY(ctx->d_H.ensure(cells * 4));
+    CUDA_TRY(ctx->d_pv.ensure(cells * 8));
+    CUDA_TRY(ctx->d_records.ensure(sizeof(dto_b200_record)));
+    CUDA_TRY(launch_full_grid(P, ctx->d_pb.as<uint16_t>(), ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), nullptr, ctx->stream));
+    CUDA_TRY(launch_full_argmin(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), 0u, ctx->d_records.as<dto_b200_record>(), ctx->stream));
+    ctx->stats.kernel_launches += 5;
+    ctx->stats.tasks_full += 1;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(cudaMemcpy(record_out, ctx->d_records.p, sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
     ctx->stats.d2h_bytes += sizeof(dto_b200_record);
     return DTO_B200_OK;

@@ -351,6 +351,54 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
 }
 
 // ---------------------------------------------------------------------------------------------------
+// batched list pairs: the CLI run of src/main.rs:91-165 once per pair, pairs sharded over GPUs
+// ---------------------------------------------------------------------------------------------------
+int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200_ranked_list *const *lists2,
+                       const uint64_t *populations, size_t n_pairs, size_t permutations, const int *devices,
+                       size_t n_devices, uint64_t seed, dto_b200_final_result *results_out) {
+    if (n_pairs == 0) return DTO_B200_OK;
+    if (!lists1 || !lists2 || !populations || !results_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    std::vector<int> devs;
+    if (n_devices == 0 || !devices) devs.push_back(0);
+    else devs.assign(devices, devices + n_devices);
+    const size_t G = devs.size();
+    const size_t per = (n_pairs + G - 1) / G;
+    std::vector<int> rcs(G, DTO_B200_OK);
+    std::vector<std::string> errs(G);
+    auto worker = [&](size_t g) {
+        const size_t lo = std::min(g * per, n_pairs), hi = std::min(lo + per, n_pairs);
+        if (lo >= hi) return;
+        dto_b200_ctx *ctx = nullptr;
+        int rc = dto_b200_create(&ctx, devs[g]);
+        std::vector<dto_b200_record> recs(permutations + 1);
+        for (size_t q = lo; rc == DTO_B200_OK && q < hi; ++q) {
+            if (!lists1[q] || !lists2[q]) {
+                rc = fail(DTO_B200_ERR_INVALID, "null list in pair %zu", q);
+                break;
+            }
+            rc = dto_b200_load_lists(ctx, lists1[q], lists2[q], populations[q]);
+            if (rc == DTO_B200_OK) rc = dto_b200_run_unpermuted(ctx, &recs[0]);
+            if (rc == DTO_B200_OK && permutations)
+                rc = dto_b200_run_permuted_philox(ctx, seed + (uint64_t)q * 0x9E3779B97F4A7C15ull, 0, permutations, recs.data() + 1, nullptr);
+            if (rc == DTO_B200_OK) rc = dto_b200_empirical_pvalue(recs.data(), recs.size(), &results_out[q]);
+        }
+        if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
+        rcs[g] = rc;
+        dto_b200_destroy(ctx);
+    };
+    if (G == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; ++g) th.emplace_back(worker, g);
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; ++g)
+        if (rcs[g] != DTO_B200_OK) return fail(rcs[g], "device %d: %s", devs[g], errs[g].c_str());
+    return DTO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // epilogue: fdr (src/stat_operations/fdr.rs:29-60), empirical_pvalue (src/stat_operations/empirical_pvalue.rs:109-187)
 // ---------------------------------------------------------------------------------------------------
 int dto_b200_fdr(uint64_t list1_len, uint64_t list2_len, uint64_t overlap, uint64_t population, double sensitivity,

@@ -49,3 +49,26 @@ def run_multi_gpu(tasks, l1, l2, population_size, devices=None, seed: int = 0):
 
     devs = list(devices) if devices is not None else list(range(device_count()))
     return run_single_node(tasks, l1, l2, population_size, 1, devs, seed)
+
+
+def run_pairs(pairs, permutations: int, devices: Optional[Sequence[int]] = None, seed: int = 0) -> List[dict]:
+    """Batched list-pair driver (BASELINE config 4): `pairs` is a sequence of (list1, list2, population_size); each pair
+    gets the whole CLI run of src/main.rs:91-165 (unpermuted optimum, `permutations` permuted tasks, empirical p, FDR)
+    and yields the reference's JSON object as a dict.  Pairs shard over `devices`."""
+    import json
+
+    from .stat_operations import final_json
+
+    n = len(pairs)
+    L1 = (C.c_void_p * max(n, 1))(*[p[0].handle for p in pairs])
+    L2 = (C.c_void_p * max(n, 1))(*[p[1].handle for p in pairs])
+    pops = np.ascontiguousarray([int(p[2]) for p in pairs], dtype=np.uint64)
+    out = (capi.FinalResult * max(n, 1))()
+    devs = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
+    capi.check(
+        capi.lib().dto_b200_run_pairs(
+            L1, L2, pops.ctypes.data_as(C.POINTER(C.c_uint64)), n, int(permutations),
+            devs.ctypes.data_as(C.POINTER(C.c_int)) if devs.size else None, devs.size, int(seed), out,
+        )
+    )
+    return [json.loads(final_json(out[i])) for i in range(n)]

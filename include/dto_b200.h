@@ -205,6 +205,15 @@ int dto_b200_empirical_pvalue(const dto_b200_record *records, size_t n, dto_b200
  * round-trip floats.  Writes at most cap bytes incl. NUL; returns needed length in *len_out. */
 int dto_b200_final_result_json(const dto_b200_final_result *r, char *buf, size_t cap, size_t *len_out);
 
+/* Batched list-pair driver (BASELINE config 4: e.g. 2 000 TF binding x perturbation pairs): pair q is the whole CLI run
+ * of src/main.rs:91-165 on (lists1[q], lists2[q], populations[q]) -- one unpermuted task + `permutations` permuted tasks
+ * + empirical_pvalue -- and yields results_out[q].  Pairs shard over `devices` (contiguous chunks); pair q draws its
+ * permutations from Philox seed  seed + q * 0x9E3779B97F4A7C15  with ids 0..permutations-1, so results do not depend
+ * on the device list. */
+int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200_ranked_list *const *lists2,
+                       const uint64_t *populations, size_t n_pairs, size_t permutations, const int *devices,
+                       size_t n_devices, uint64_t seed, dto_b200_final_result *results_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,11 @@ def test_grid_and_unpermuted_optimum(engine, name):
     rec = engine.run_unpermuted()
     H.assert_record_matches(rec, ref.best)
     assert not (int(rec["flags"]) & dto._capi.FLAG_PERMUTED)
+    # and through the scan kernel (identity indices): same optimum
+    i1, i2 = np.arange(len(ids1), dtype=np.uint32)[None, :], np.arange(len(ids2), dtype=np.uint32)[None, :]
+    rk = engine.run_permuted_indices(i1, i2)[0]
+    if not int(rk["flags"]) & dto._capi.FLAG_NEAR_TIE:
+        H.assert_record_matches(rk, ref.best)
     if len(ids1) <= 400:  # the reference-faithful (string/HashSet/uncached) oracle agrees too
         fb = O.optimize_faithful(o1, o2, N)
         H.assert_record_matches(rec, {k: fb[k] for k in fb.dtype.names})
@@ -217,10 +222,17 @@ def test_underflow_plateau_tiebreak(engine):
     rec = engine.run_unpermuted()
     assert float(rec["pvalue"]) == 0.0
     H.assert_record_matches(rec, ref.best)
+    # the same task through the warp-per-permutation scan kernel (identity "permutation"): plateau logic of K1
+    ident = np.arange(N, dtype=np.uint32)[None, :]
+    rk = engine.run_permuted_indices(ident, ident)[0]
+    assert float(rk["pvalue"]) == 0.0
+    H.assert_record_matches(rk, ref.best)
     # near-identical: 2% of list 2 perturbed
     ids1, r1, ids2, r2 = H.synthetic_pair(N, 4, 0.002)
     o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
-    H.assert_record_matches(engine.run_unpermuted(), O.grid_int(o1, o2, pop, slot).best)
+    want = O.grid_int(o1, o2, pop, slot).best
+    H.assert_record_matches(engine.run_unpermuted(), want)
+    H.assert_record_matches(engine.run_permuted_indices(ident, ident)[0], want)
 
 
 def test_degenerate_and_error_paths(engine):
@@ -380,3 +392,29 @@ def test_background_subset_config_c5_small(engine):
     for t in range(12):
         if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
             H.assert_record_matches(recs[t], O.grid_int(o1, o2, N, slot, p1[t], p2[t], want_overlap=False, want_p=False).best)
+
+
+def test_batched_pairs_driver(engine):
+    """BASELINE configs[3] at reduced size: many independent list pairs, each = unpermuted optimum + permutation null
+    + epilogue; sharding over contexts does not change any result."""
+    pairs, want = [], []
+    for q in range(6):
+        ids1, r1, ids2, r2 = H.synthetic_pair(300 + 40 * q, 1000 + q, 0.35 if q % 2 else None)
+        l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+        pairs.append((l1, l2, dto.compute_population_size(l1, l2, None)))
+        o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+        want.append(O.grid_int(o1, o2, len(ids1)).best)
+    a = dto.run_pairs(pairs, 400, devices=[0], seed=9)
+    b = dto.run_pairs(pairs, 400, devices=[0, 0, 0], seed=9)  # three contexts on the same GPU: same sharding code path
+    assert a == b
+    for q, (res, ob) in enumerate(zip(a, want)):
+        assert (res["rank1"], res["rank2"], res["set1_len"], res["set2_len"], res["unpermuted_intersection_size"]) == (
+            int(ob["rank1"]), int(ob["rank2"]), int(ob["set1_len"]), int(ob["set2_len"]), int(ob["intersection_size"]))
+        assert res["unpermuted_pvalue"] == pytest.approx(float(ob["pvalue"]), rel=1e-12)
+        assert res["fdr"] == O.fdr(int(ob["set1_len"]), int(ob["set2_len"]), int(ob["intersection_size"]), pairs[q][2], 0.8)
+        assert 0.0 <= res["empirical_pvalue"] <= 1.0
+        if q % 2:  # concordant pairs are significant against their own null
+            assert res["empirical_pvalue"] <= 0.01
+    # null pairs: the empirical p of a null pair is roughly uniform -- at least not all tiny
+    assert max(a[q]["empirical_pvalue"] for q in (0, 2, 4)) > 0.05
+    assert dto.run_pairs(pairs, 400, seed=10) != a
