@@ -36,10 +36,12 @@ constexpr double kZeroHi = -745.12;
 struct Problem {
     int T1, T2;
     int CH;          // columns per lane in the scan kernel (template value actually used)
-    int CHP;         // CH | 1: padded stride of the per-warp row histogram (conflict-free LDS)
+    int CHP;         // CH + 2: padded stride (words) of the per-warp row histogram: even for 64-bit column pairs
     int T2pad;       // 32 * CH
     int levels;      // number of screen levels beyond level 0
     int debug_task;  // diagnostics: task index whose refined cells are printed (-1 = off)
+    uint32_t never;  // kcrit value meaning "no overlap passes": 0x7FFF when every set size is <= 32766 (packed 15-bit
+                     // screen), else 0xFFFF
     uint32_t n1, n2;
     uint32_t n1_eff;     // #list-1 positions whose rank is <= the last threshold of list 1
     uint32_t pb_stride;  // u16 elements per permutation row of the partner-bin array
@@ -51,7 +53,7 @@ struct Problem {
     const double *lf;    // [N+1] ln_factorial
     const double *rowA;  // [T1] lf[K] + lf[N-K]
     const double *colB;  // [T2] lf[n] + lf[N-n] - lf[N]
-    const uint16_t *kcrit;     // [(levels+1)][T1][T2pad], column j stored at (j % CH) * 32 + j / CH
+    const uint16_t *kcrit;     // [(levels+1)][T1][T2pad], column j stored at kcrit_col(j, CH)
     const uint2 *cellmeta;     // [T1*T2] {offset into lptab, kbase | count << 16}: log p tabulated for k in [kbase, kbase+count)
     const double *lptab;       // log p (ratio-recurrence tail, ~1e-10) for every (cell, k) between tau_1 and tau_levels
     const uint16_t *dslot2;    // [n2] row-histogram slot of list-2 position (or kNoSlot)
@@ -60,6 +62,13 @@ struct Problem {
     const int32_t *slot2_of_1; // [n1]
     double level_log[kMaxLevels + 1];  // log tau_l ; [0] = +inf
 };
+
+// Position of column j inside a kcrit row: lane = j / CH owns columns m = j % CH; its pair m/2 is one 32-bit word and
+// the words of pair q are contiguous across lanes, so a warp reads a row with CH/2 coalesced 128-byte loads.
+__host__ __device__ inline size_t kcrit_col(int j, int CH) {
+    const int lane = j / CH, m = j % CH;
+    return ((size_t)(m >> 1) * 32 + (size_t)lane) * 2 + (size_t)(m & 1);
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  Counter-based: the permutation for (seed, perm id) is a pure

@@ -101,11 +101,12 @@ struct dto_b200_ctx {
         d_err, d_pair, d_minp, d_tstats, d_words;
     bool opt_task_stats = false;
     int opt_debug_task = -1;
+    bool opt_swar = true;
     int last_batch_n = 0;
     PinnedBuf h_records, h_status, h_stage;
     // options
     int opt_batch = 0;  // 0 = auto
-    int opt_warps = 8;
+    int opt_warps = kScanThreads / 32;
     int opt_levels = 32;
     dto_b200_stats stats{};
 };
@@ -283,11 +284,14 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
         if (value < 0 || value > (1 << 22)) return fail(DTO_B200_ERR_INVALID, "batch out of range");
         ctx->opt_batch = (int)value;
     } else if (s == "warps_per_cta") {
-        if (value < 1 || value > kScanThreads / 32) return fail(DTO_B200_ERR_INVALID, "warps_per_cta must be 1..8");
+        if (value < 1 || value > kScanThreads / 32) return fail(DTO_B200_ERR_INVALID, "warps_per_cta out of range");
         ctx->opt_warps = (int)value;
     } else if (s == "debug_task") {
         ctx->opt_debug_task = (int)value;
         ctx->P.debug_task = (int)value;
+    } else if (s == "packed_screen") {
+        if (ctx->has_problem) return fail(DTO_B200_ERR_STATE, "set 'packed_screen' before dto_b200_set_problem");
+        ctx->opt_swar = value != 0;
     } else if (s == "task_stats") {
         ctx->opt_task_stats = value != 0;
     } else if (s == "levels") {
@@ -371,7 +375,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.T1 = (int)T1;
     P.T2 = (int)T2;
     P.CH = pick_ch((int)T2);
-    P.CHP = P.CH | 1;
+    P.CHP = P.CH + 2;
     P.T2pad = 32 * P.CH;
     P.levels = ctx->opt_levels;
     P.debug_task = ctx->opt_debug_task;
@@ -388,6 +392,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
                     "(%llu)",
                     c1[T1 - 1], c2[T2 - 1], (unsigned long long)population);
     P.n1_eff = c1[T1 - 1];
+    P.never = (ctx->opt_swar && c1[T1 - 1] <= 32766u && c2[T2 - 1] <= 32766u) ? 0x7FFFu : 0xFFFFu;
     P.pb_stride = ((P.n1_eff + 1 + 255) / 256) * 256;  // whole staging chunks (cp.async in the scan), 512 B aligned rows
     std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(n2 ? n2 : 1);
     for (size_t j = 0; j < n1; ++j) {

@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
         tab_n = m.y >> 16;
         if (tab_n == 0) return;
     }
-    uint32_t kc1 = 0xFFFFu, kcL = 0xFFFFu;  // mode 0: kcrit at level 1 and at the deepest level
-    const size_t col = (size_t)(j % P.CH) * 32 + (size_t)(j / P.CH);
+    const uint32_t never = P.never;  // "no overlap passes": 0xFFFF, or 0x7FFF when the packed 15-bit screen is in use
+    uint32_t kc1 = never, kcL = never;  // pass 0: kcrit at level 1 and at the deepest level
+    const size_t col = kcrit_col(j, P.CH);
     const size_t level_stride = (size_t)P.T1 * P.T2pad;
     uint16_t *dst = kcrit + (size_t)i * P.T2pad + col;
     if (pass == 0) dst[0] = (uint16_t)(lower + 1);  // level 0: every cell the reference does not short-circuit to p = 1
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
             if (k <= tab_lo) break;
         } else {
             while (l >= 1 && S > exp(P.level_log[l]) * (1.0 + 1e-6)) {
-                const uint16_t v = (k + 1 <= upper) ? (uint16_t)(k + 1) : kNoSlot;
+                const uint16_t v = (k + 1 <= upper) ? (uint16_t)(k + 1) : (uint16_t)never;
                 dst[l * level_stride] = v;
                 if (l == P.levels) kcL = v;
                 if (l == 1) kc1 = v;
@@ -108,13 +109,17 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
         // tabulate k in [kc1, min(kcL, upper + 1)): cells the screen can pass at levels 1 .. levels-1; deeper (k >= kcL)
         // or shallower (k < kc1, only reachable at level 0) cells take the closed-form / recurrence path in the scan
         uint32_t cnt = 0;
-        if (P.levels >= 2 && kc1 != 0xFFFFu) {
-            const uint32_t hi = (kcL == 0xFFFFu) ? (uint32_t)upper + 1u : (uint32_t)kcL;
+        if (P.levels >= 2 && kc1 != never) {
+            const uint32_t hi = (kcL == never) ? (uint32_t)upper + 1u : (uint32_t)kcL;
             cnt = hi > kc1 ? hi - kc1 : 0u;
         }
         counts[cell] = cnt;
         meta[cell] = make_uint2(0u, (uint32_t)kc1 | (cnt << 16));
     }
+}
+
+__global__ void fill_u16_kernel(uint16_t *__restrict__ dst, size_t n, uint16_t v) {
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) dst[x] = v;
 }
 
 __global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ offsets, uint2 *__restrict__ meta) {
@@ -405,8 +410,8 @@ struct __align__(16) Cand {
 
 template <int CH>
 struct ScanLayout {
-    static constexpr int CHP = CH | 1;
-    static constexpr int HALF = (CH + 1) / 2;    // the screen loop checks the queue after HALF columns
+    static constexpr int CHP = CH + 2;           // even (64-bit column pairs) and CHP/2 odd for CH % 4 == 0
+    static constexpr int HALF = 2 * ((CH / 2 + 1) / 2);  // the screen loop checks the queue after HALF columns
     static constexpr int QCAP = 32 * HALF + 64;  // < 32 left-overs + one half row, rounded up
     static constexpr int CAP = kCandCap;
     static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
@@ -691,7 +696,7 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
     __syncwarp();
 }
 
-template <int CH>
+template <int CH, bool SWAR>
 __global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : kScanCtasPerSm)
 scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
             dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
@@ -744,9 +749,11 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         R.cand = cand;
         R.lane = lane;
 
-        uint32_t kcur[CH];
+        // overlap counts of this lane's CH columns, two 16-bit counts per register (k <= 65534 by the list-size limit)
+        constexpr int NP = CH / 2;
+        uint32_t kcur2[NP];
 #pragma unroll
-        for (int m = 0; m < CH; ++m) kcur[m] = 0;
+        for (int q = 0; q < NP; ++q) kcur2[q] = 0;
         uint32_t koff = 0;
         int level = 0;
 
@@ -767,13 +774,16 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         __syncwarp();
         issue_chunk(2);
         uint32_t cbase = 0, lo = 0;
+        uint2 *D2 = reinterpret_cast<uint2 *>(D + lane * CHP);  // this lane's column pairs (8-byte aligned: CHP even)
         for (int i = 0; i < P.T1; ++i) {
             const uint32_t hi = s_c1[i];
-            // critical overlaps of this row at the current screen level (in flight during the scatter)
-            const uint16_t *__restrict__ kr = P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad + lane;
-            uint32_t kc[CH];
+            // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
+            // the scatter)
+            const uint32_t *__restrict__ kr =
+                reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
+            uint32_t kc2[NP];
 #pragma unroll
-            for (int m = 0; m < CH; ++m) kc[m] = __ldg(kr + m * 32);
+            for (int q = 0; q < NP; ++q) kc2[q] = __ldg(kr + q * 32);
             // (1) bin this row's genes: position -> partner's column slot, privatised per warp
             while (lo < hi) {
                 if ((lo / kChunk) > cbase) {  // chunk cbase is consumed: cbase+2 must have landed, refill its slot
@@ -795,11 +805,12 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
             // (2) 2-D inclusive prefix: lane-local run over its CH columns + warp exclusive scan of lane totals
             uint32_t run = 0;
 #pragma unroll
-            for (int m = 0; m < CH; ++m) {
-                const uint32_t d = D[lane * CHP + m];
-                D[lane * CHP + m] = 0;
-                run += d;
-                kcur[m] += run;
+            for (int q = 0; q < NP; ++q) {
+                const uint2 d = D2[q];
+                D2[q] = make_uint2(0u, 0u);
+                const uint32_t r0 = run + d.x;
+                run = r0 + d.y;
+                kcur2[q] += r0 + (run << 16);
             }
             uint32_t inc = run;
 #pragma unroll
@@ -808,26 +819,50 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 if (lane >= o) inc += v;
             }
             koff += inc - run;
+            const uint32_t koff2 = koff * 0x10001u;
             // (3) screen: only k >= kcrit can have p <= tau_level.  Two halves so the queue only needs half a row.
-#pragma unroll
-            for (int m = 0; m < L::HALF; ++m) {
-                const uint32_t k = kcur[m] + koff;
-                if (k >= kc[m]) {
+            auto screen = [&](int q) {
+                const uint32_t kk = kcur2[q] + koff2;  // no carry between the halves: every k < 65536
+                const uint32_t k0 = kk & 0xFFFFu, k1 = kk >> 16;
+                if (k0 >= (kc2[q] & 0xFFFFu)) {
                     const uint32_t slot = atomicAdd(qcnt, 1u);
-                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + m);
-                    Qk[slot] = (uint16_t)k;
+                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q);
+                    Qk[slot] = (uint16_t)k0;
                 }
-            }
-            __syncwarp();
-            if (*qcnt >= 32) level = drain_queue(P, R, false, level);
-#pragma unroll
-            for (int m = L::HALF; m < CH; ++m) {
-                const uint32_t k = kcur[m] + koff;
-                if (k >= kc[m]) {
+                if (k1 >= (kc2[q] >> 16)) {
                     const uint32_t slot = atomicAdd(qcnt, 1u);
-                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + m);
-                    Qk[slot] = (uint16_t)k;
+                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q + 1);
+                    Qk[slot] = (uint16_t)k1;
                 }
+            };
+            constexpr int NH = (NP + 1) / 2;
+            if constexpr (SWAR) {
+                // packed 15-bit compare, branch-free: field = k + 0x8000 - kcrit keeps its top bit iff k >= kcrit (all
+                // values < 0x8000, "never" = 0x7FFF, so no borrow crosses the fields); one test per half row
+                const uint32_t bias = koff2 + 0x80008000u;
+                uint32_t hit = 0;
+#pragma unroll
+                for (int q = 0; q < NH; ++q) hit |= (kcur2[q] + bias - kc2[q]);
+                if (hit & 0x80008000u) {
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) screen(q);
+                }
+                __syncwarp();
+                if (*qcnt >= 32) level = drain_queue(P, R, false, level);
+                hit = 0;
+#pragma unroll
+                for (int q = NH; q < NP; ++q) hit |= (kcur2[q] + bias - kc2[q]);
+                if (hit & 0x80008000u) {
+#pragma unroll
+                    for (int q = NH; q < NP; ++q) screen(q);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < NH; ++q) screen(q);
+                __syncwarp();
+                if (*qcnt >= 32) level = drain_queue(P, R, false, level);
+#pragma unroll
+                for (int q = NH; q < NP; ++q) screen(q);
             }
             __syncwarp();
             if (*qcnt >= 32) level = drain_queue(P, R, false, level);
@@ -949,13 +984,13 @@ __global__ void hbm_copy_probe_kernel(const uint4 *__restrict__ src, uint4 *__re
 // =====================================================================================================
 // launchers
 // =====================================================================================================
-template <int CH>
+template <int CH, bool SWAR>
 static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags,
                                  dto_b200_record *out, uint32_t *status, unsigned long long *counters,
                                  uint32_t *task_stats, int grid, int warps, cudaStream_t st) {
     using L = ScanLayout<CH>;
     const size_t smem = (((size_t)P.T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * L::per_warp;
-    auto kern = scan_kernel<CH>;
+    auto kern = scan_kernel<CH, SWAR>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, st>>>(P, pb, n_tasks, flags, out, status, counters, task_stats);
@@ -963,15 +998,15 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
 }
 
 size_t scan_smem_bytes(int CH, int T1, int warps) {
-    const size_t chp = (size_t)(CH | 1);
+    const size_t chp = (size_t)(CH + 2);
     const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
-    const size_t q = ((size_t)(32 * ((CH + 1) / 2) + 64) * 6 + 15) & ~(size_t)15;
+    const size_t q = ((size_t)(32 * (2 * ((CH / 2 + 1) / 2)) + 64) * 6 + 15) & ~(size_t)15;
     const size_t per = d + q + 16 + (size_t)kCandCap * sizeof(Cand) + (size_t)kRing * 2;
     return (((size_t)T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * per;
 }
 
 int pick_ch(int T2) {
-    static const int opts[] = {1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 48, 64};
+    static const int opts[] = {2, 4, 8, 12, 16, 20, 24, 28, 32, 48, 64};
     const int need = (T2 + 31) / 32;
     for (int o : opts)
         if (o >= need) return o;
@@ -981,11 +1016,13 @@ int pick_ch(int T2) {
 cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags, dto_b200_record *out,
                         uint32_t *status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
                         cudaStream_t st) {
-#define DTO_CASE(X) \
-    case X:         \
-        return launch_scan_t<X>(P, pb, n_tasks, flags, out, status, counters, task_stats, grid, warps, st);
+#define DTO_CASE(X)                                                                                                 \
+    case X:                                                                                                         \
+        return P.never == 0x7FFFu                                                                                   \
+                   ? launch_scan_t<X, true>(P, pb, n_tasks, flags, out, status, counters, task_stats, grid, warps, st) \
+                   : launch_scan_t<X, false>(P, pb, n_tasks, flags, out, status, counters, task_stats, grid, warps, st);
     switch (P.CH) {
-        DTO_CASE(1) DTO_CASE(2) DTO_CASE(4) DTO_CASE(8) DTO_CASE(12) DTO_CASE(16) DTO_CASE(20) DTO_CASE(24)
+        DTO_CASE(2) DTO_CASE(4) DTO_CASE(8) DTO_CASE(12) DTO_CASE(16) DTO_CASE(20) DTO_CASE(24)
         DTO_CASE(28) DTO_CASE(32) DTO_CASE(48) DTO_CASE(64)
         default:
             return cudaErrorInvalidValue;
@@ -994,8 +1031,9 @@ cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint3
 }
 
 cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *counts, uint2 *meta, cudaStream_t st) {
-    const size_t bytes = (size_t)(P.levels + 1) * P.T1 * P.T2pad * sizeof(uint16_t);
-    cudaError_t e = cudaMemsetAsync(kcrit, 0xFF, bytes, st);
+    const size_t words = (size_t)(P.levels + 1) * P.T1 * P.T2pad;
+    fill_u16_kernel<<<1024, 256, 0, st>>>(kcrit, words, (uint16_t)P.never);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int cells = P.T1 * P.T2;
     e = cudaMemsetAsync(meta, 0, (size_t)cells * sizeof(uint2), st);

@@ -418,3 +418,39 @@ def test_batched_pairs_driver(engine):
     # null pairs: the empirical p of a null pair is roughly uniform -- at least not all tiny
     assert max(a[q]["empirical_pvalue"] for q in (0, 2, 4)) > 0.05
     assert dto.run_pairs(pairs, 400, seed=10) != a
+
+
+def test_generic_and_packed_screen_agree(engine, built):
+    """The scan kernel has two screen code paths: packed 15-bit (set sizes <= 32766) and generic 16-bit (longer lists).
+    Both must give identical records; the generic one is also what lists longer than 32 766 features use."""
+    ids1, r1, ids2, r2 = H.synthetic_pair(3000, 77, 0.3)
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    engine.load_lists(l1, l2, 3000)
+    a = engine.run_permuted_philox(5, 0, 3000)
+    with dto.Engine(0) as e2:
+        e2.set_option("packed_screen", 0)
+        e2.load_lists(l1, l2, 3000)
+        b = e2.run_permuted_philox(5, 0, 3000)
+        ident = np.arange(3000, dtype=np.uint32)[None, :]
+        u = e2.run_permuted_indices(ident, ident)[0]
+    assert np.array_equal(a, b)
+    o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+    H.assert_record_matches(u, O.grid_int(o1, o2, 3000).best)
+
+
+def test_long_lists_generic_path(engine):
+    """40 000-feature lists (> 32 766: generic screen, sort buffer in the global scratch): a few permutations replayed
+    through the oracle."""
+    N = 40000
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, 4, None)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    assert engine.shape[:2] == (659, 659)
+    lf = O.ln_factorial_table(pop)
+    recs = engine.run_permuted_philox(3, 0, 64)
+    for t in (0, 63):
+        pairing = engine.philox_pairing(3, t)
+        assert np.array_equal(np.sort(pairing), np.arange(N))
+        p1, p2 = H.perms_from_pairing(pairing, slot, N)
+        ob = O.grid_int(o1, o2, pop, slot, p1, p2, lf=lf, want_overlap=False, want_p=False).best
+        if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            H.assert_record_matches(recs[t], ob)
