@@ -70,5 +70,40 @@ def main(rep, tasks):
         print(f"{key[0][:16]:16s}:{key[1]:4d}  samp {100 * a[0] / ts:5.1f}%  inst {100 * a[1] / ti:5.1f}%  {src[key].strip()[:100]}")
 
 
+def to_json(rep, tasks, out_path):
+    """Key per-launch figures of one captured launch, for bench.py's roofline object (static evidence, not live)."""
+    import json
+
+    raw = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "raw", "--csv"]))))
+    hdr, units, vals = raw[0], raw[1], raw[2]
+    m = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+
+    def f(k):
+        return float(m[k][0])
+
+    d = {
+        "source": rep.split("/")[-1], "permutations_in_launch": tasks,
+        "dram_bytes_per_permutation": (f("dram__bytes_read.sum") * scale.get(m["dram__bytes_read.sum"][1], 1) +
+                                       f("dram__bytes_write.sum") * scale.get(m["dram__bytes_write.sum"][1], 1)) / tasks,
+        "warp_instructions_per_permutation": f("smsp__inst_executed.sum") / tasks,
+        "issue_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "warps_active_pct": f("sm__warps_active.avg.pct_of_peak_sustained_active"),
+        "fp64_pipe_pct": f("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+        "lsu_pipe_pct": f("sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active"),
+        "alu_pipe_pct": f("sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active"),
+        "shared_wavefronts_pct_of_peak": f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+        "shared_atomic_instructions_per_permutation": f("smsp__inst_executed_op_shared_atom.sum") / tasks,
+        "dram_throughput_pct": f("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+        "registers_per_thread": f("launch__registers_per_thread"),
+        "top_stalls": {h[len(STALLS):-len("_per_issue_active.ratio")]: float(m[h][0]) for h in hdr
+                       if h.startswith(STALLS) and h.endswith("_per_issue_active.ratio") and float(m[h][0]) > 0.2 and "selected" not in h},
+    }
+    json.dump(d, open(out_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]))
+    if len(sys.argv) > 3:
+        to_json(sys.argv[1], int(sys.argv[2]), sys.argv[3])
+    else:
+        main(sys.argv[1], int(sys.argv[2]))
