@@ -454,3 +454,27 @@ def test_long_lists_generic_path(engine):
         ob = O.grid_int(o1, o2, pop, slot, p1, p2, lf=lf, want_overlap=False, want_p=False).best
         if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
             H.assert_record_matches(recs[t], ob)
+
+
+def test_huge_rank_values_many_thresholds(engine):
+    """Ranks are arbitrary u32 values (gaps, rank 0): a 300-feature list whose ranks reach 5e8 has ~1 650 thresholds
+    per list (CH = 64 kernel variant, mostly empty rows)."""
+    rng = np.random.default_rng(5)
+    n = 300
+    ids = H.ids_for(n, "h")
+    r1 = np.sort(rng.integers(0, 500_000_000, size=n)).astype(np.uint32)
+    r2 = rng.permutation(np.sort(rng.integers(1, 400_000_000, size=n))).astype(np.uint32)
+    o1, o2, N, slot = load(engine, ids, r1, list(ids), r2)
+    assert o1.thresholds.size > 1500 and o2.thresholds.size > 1500
+    ref = O.grid_int(o1, o2, N, slot)
+    ov, pv, _ = engine.grid_debug()
+    assert np.array_equal(ov, ref.overlap)
+    assert np.allclose(pv, ref.p, rtol=1e-12, atol=0)
+    H.assert_record_matches(engine.run_unpermuted(), ref.best)
+    p1, p2 = H.perms(n, 10, 1), H.perms(n, 10, 2)
+    recs = engine.run_permuted_indices(p1, p2)
+    for t in range(10):
+        if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+            H.assert_record_matches(recs[t], O.grid_int(o1, o2, N, slot, p1[t], p2[t], want_overlap=False, want_p=False).best)
+    ph = engine.run_permuted_philox(1, 0, 50)
+    assert np.all((ph["pvalue"] > 0) & (ph["pvalue"] <= 1.0))

@@ -154,3 +154,25 @@ def test_no_cpu_fallback_without_gpu():
         if mod.endswith(".py"):
             assert "oracle" not in open(os.path.join(H.ROOT, "dual_threshold_optimization_b200", mod)).read().replace("no oracle", ""), mod
     assert "oracle" not in src
+
+
+def test_c_abi_argument_validation():
+    """Entry points validate their arguments before touching CUDA and report through dto_b200_last_error()."""
+    L = capi.lib()
+    assert L.dto_b200_fdr(1, 1, 1, 1, 0.8, None) == capi.ERR_INVALID
+    assert b"null" in L.dto_b200_last_error()
+    assert L.dto_b200_ranked_list_from(None, None, 0, None) == capi.ERR_INVALID
+    assert L.dto_b200_create(None, 0) == capi.ERR_INVALID
+    assert L.dto_b200_set_problem(None, None, 0, None, 0, None, 0, None, 0, None, 0) == capi.ERR_INVALID
+    assert L.dto_b200_run_unpermuted(None, None) == capi.ERR_INVALID
+    assert L.dto_b200_device_count(None) == capi.ERR_INVALID
+    assert L.dto_b200_empirical_pvalue(None, 3, None) == capi.ERR_INVALID
+    assert L.dto_b200_run_single_node(None, None, 1, None, 1, None, 0, 0, None) == capi.ERR_INVALID
+    assert L.dto_b200_run_pairs(None, None, None, 1, 1, None, 0, 0, None) == capi.ERR_INVALID
+    assert L.dto_b200_run_pairs(None, None, None, 0, 1, None, 0, 0, None) == capi.OK  # zero pairs: nothing to do
+    assert L.dto_b200_compute_population_size(None, None, None, None) == capi.ERR_INVALID
+    h = C.c_void_p()
+    assert L.dto_b200_read_ranked_list_csv(b"/nonexistent/file.csv", C.byref(h)) == capi.ERR_IO
+    L.dto_b200_destroy(None)  # no-op
+    L.dto_b200_ranked_list_free(None)
+    L.dto_b200_feature_list_free(None)
