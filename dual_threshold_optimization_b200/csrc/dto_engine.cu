@@ -549,17 +549,15 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
     if (Pn == 0) return DTO_B200_OK;
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    // lists too long for the in-shared-memory sort buffer keep it in a per-CTA global scratch (L2-resident)
-    const bool words_in_smem = sigma_smem_bytes(P, B1, B2, true) <= ctx->smem_optin;
+    // The sort buffer + boundary list of the pairing kernel live in a per-CTA global scratch (2 x nmax words, L2-
+    // resident): the row-wise fast path touches it for ~4 % of the elements only, and long lists would not fit it in
+    // shared memory anyway.
     if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel needs %zu B of shared memory (> %zu)",
                     sigma_smem_bytes(P, B1, B2, false), ctx->smem_optin);
-    const int sigma_grid_max = ctx->sm_count * (words_in_smem ? 4 : 1);
-    uint32_t *words_scratch = nullptr;
-    if (!words_in_smem) {
-        CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * std::max(P.n1, P.n2) * 4));
-        words_scratch = ctx->d_words.as<uint32_t>();
-    }
+    const int sigma_grid_max = ctx->sm_count * 4;
+    CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * 2 * std::max(P.n1, P.n2) * 4));
+    uint32_t *words_scratch = ctx->d_words.as<uint32_t>();
     const size_t batch = (size_t)auto_batch(ctx);
     ctx->stats.last_scan_kernel_ms = 0;
     ctx->stats.last_sigma_kernel_ms = 0;
@@ -630,14 +628,10 @@ int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, 
     if (!pos2_of_pos1_out) return fail(DTO_B200_ERR_INVALID, "null output");
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    const bool words_in_smem = sigma_smem_bytes(P, B1, B2, true) <= ctx->smem_optin;
     if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel does not fit shared memory");
-    uint32_t *words_scratch = nullptr;
-    if (!words_in_smem) {
-        CUDA_TRY(ctx->d_words.ensure((size_t)std::max(P.n1, P.n2) * 4));
-        words_scratch = ctx->d_words.as<uint32_t>();
-    }
+    CUDA_TRY(ctx->d_words.ensure((size_t)2 * std::max(P.n1, P.n2) * 4));
+    uint32_t *words_scratch = ctx->d_words.as<uint32_t>();
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
     CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_pair.p, 0xFF, (size_t)(P.n1 ? P.n1 : 1) * 4, ctx->stream));

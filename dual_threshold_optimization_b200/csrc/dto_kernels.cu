@@ -138,8 +138,9 @@ __global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ 
 struct SortShared {
     uint32_t *words;     // [n]     (rem16 << 16) | element, bucket-contiguous
     uint32_t *cnt;       // [NB+1]  bucket counts, then offsets (exclusive scan)
-    uint16_t *arrival;   // [n]     arrival slot inside the bucket (aliases the staged output row)
-    uint32_t *scan_tmp;  // [32]
+    uint16_t *arrival;   // [n]     arrival slot inside the bucket
+    uint32_t *scan_tmp;  // [33]: [0..31] warp partials of the block scan, [32] = boundary-list counter
+    uint32_t *list;      // [n]     (global scratch) elements of buckets that straddle a row boundary: bucket << 16 | element
 };
 
 __device__ __forceinline__ void philox_keys(uint32_t (&out)[4], uint64_t seed, uint64_t perm_id, uint32_t stream,
@@ -299,6 +300,69 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
     __syncthreads();
 }
 
+// Fast path when only the ROW of every list-1 position matters (identical gene sets, no export): positions inside one
+// threshold row are interchangeable for the overlap grid, so an element whose whole bucket lies inside one row takes
+// position off[bucket] + arrival without being ranked (no third key pass, no sort-buffer traffic).  Only the ~4 % of
+// elements in buckets that straddle a row boundary are ranked exactly (words/list in the global scratch).  The result
+// is a uniform permutation up to within-row order; the records it leads to are identical to the exact path's.
+__device__ void block_place_rowwise(const SortShared &S, const Problem &P, uint32_t n, int B, uint64_t seed,
+                                    uint64_t perm_id, uint32_t stream, uint16_t *stage) {
+    const uint32_t NB = 1u << B;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t x = tid; x <= NB; x += nt) S.cnt[x] = 0;
+    if (tid == 0) S.scan_tmp[32] = 0;
+    __syncthreads();
+    const uint32_t nblk = (n + 3) >> 2;
+    for (uint32_t c = tid; c < nblk; c += nt) {
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = c * 4 + q;
+            if (e < n) S.arrival[e] = (uint16_t)atomicAdd(&S.cnt[key[q] >> (32 - B)], 1u);
+        }
+    }
+    __syncthreads();
+    block_exclusive_scan(S.cnt, NB, S.scan_tmp);
+    for (uint32_t c = tid; c < nblk; c += nt) {
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = c * 4 + q;
+            if (e < n) {
+                const uint32_t b = key[q] >> (32 - B);
+                const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
+                const uint32_t pos = lo + S.arrival[e];
+                if (P.bin1[lo] == P.bin1[hi - 1]) {
+                    if (pos < P.n1_eff) stage[pos] = P.dslot2[e];
+                } else {
+                    S.words[pos] = (((key[q] >> (16 - B)) & 0xFFFFu) << 16) | e;
+                    S.list[atomicAdd(&S.scan_tmp[32], 1u)] = (b << 16) | e;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_list = S.scan_tmp[32];
+    for (uint32_t x = tid; x < n_list; x += nt) {
+        const uint32_t ent = S.list[x];
+        const uint32_t e = ent & 0xFFFFu, b = ent >> 16;
+        const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
+        const uint32_t rem = S.words[lo + S.arrival[e]] >> 16;
+        uint32_t rank = 0;
+        bool tie = false;
+        for (uint32_t y = lo; y < hi; ++y) {
+            const uint32_t v = S.words[y];
+            rank += ((v >> 16) < rem) ? 1u : 0u;
+            tie = tie || ((v >> 16) == rem && (v & 0xFFFFu) != e);
+        }
+        if (tie) rank = rank_with_ties(S.words, lo, hi, e, rem, seed, perm_id, stream);
+        if (lo + rank < P.n1_eff) stage[lo + rank] = P.dslot2[e];
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed,
                                                                    uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
@@ -307,26 +371,30 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
-    // layout: cnt[NB+1] | scan_tmp[33] | stage[max(pb_stride, nmax)] u16 | order2[n_common] u16 | words[nmax] u32 (or global)
+    // layout: cnt[NB+1] | scan_tmp[33] | stage[stage_len] u16 | arrival[nmax] u16 | order2[n_common] u16 | words[nmax] u32
+    // (words and the boundary list live in the per-CTA global scratch when it is given)
     SortShared S;
     S.cnt = reinterpret_cast<uint32_t *>(smem_raw);
     S.scan_tmp = S.cnt + (1u << Bmax) + 1;
-    const uint32_t stage_len = P.pb_stride > nmax ? P.pb_stride : nmax;
+    const uint32_t stage_len = P.pb_stride;
     uint16_t *stage = reinterpret_cast<uint16_t *>(S.scan_tmp + 33);  // (NB + 1 + 33) words: 8-byte aligned for B >= 1
-    S.arrival = stage;  // dead before the staged output row is written
+    S.arrival = stage + stage_len;                                    // pb_stride is a multiple of 256
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
-    uint16_t *order2 = stage + ((stage_len + 1) & ~1u);
-    uint16_t *after = order2 + (identical ? 0u : ((P.n_common + 1) & ~1u));
-    S.words = words_scratch ? words_scratch + (size_t)blockIdx.x * nmax
-                            : reinterpret_cast<uint32_t *>(after + ((4 - ((uintptr_t)after & 3)) & 3) / 2);
+    uint16_t *order2 = S.arrival + ((nmax + 3) & ~3u);
+    uint16_t *after = order2 + (identical ? 0u : ((P.n_common + 3) & ~3u));
+    S.words = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax : reinterpret_cast<uint32_t *>(after);
+    S.list = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax + nmax : nullptr;
+    const bool rowwise = identical && pairing_out == nullptr && words_scratch != nullptr;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
 
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const uint64_t perm_id = first_id + (uint64_t)t;
         uint16_t *dst = pb + (size_t)t * P.pb_stride;
-        if (identical) {
-            // element = list-2 position e, rank f = the list-1 position it is paired with.  The emit of pass 4 must not
-            // overwrite `arrival` (aliased with the staging row) -- pass 3 has consumed it by then.
+        if (rowwise) {
+            block_place_rowwise(S, P, P.n2, B2, seed, perm_id, 0u, stage);
+            for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
+        } else if (identical) {
+            // element = list-2 position e, rank f = the list-1 position it is paired with
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
                 if (f < P.n1_eff) stage[f] = P.dslot2[e];
                 if (pairing_out) pairing_out[(size_t)t * P.n1 + f] = e;
@@ -1053,12 +1121,11 @@ cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *
 size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem) {
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
-    const uint32_t stage_len = P.pb_stride > nmax ? P.pb_stride : nmax;
     size_t b = ((size_t)(1u << Bmax) + 1 + 33) * 4;
-    b += (size_t)((stage_len + 1) & ~1u) * 2;
+    b += (size_t)P.pb_stride * 2;
+    b += (size_t)((nmax + 3) & ~3u) * 2;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
-    if (!identical) b += (size_t)((P.n_common + 1) & ~1u) * 2;
-    b += 4;
+    if (!identical) b += (size_t)((P.n_common + 3) & ~3u) * 2;
     if (words_in_smem) b += (size_t)nmax * 4;
     return (b + 15) & ~(size_t)15;
 }
