@@ -60,6 +60,7 @@ struct Problem {
     const uint16_t *bin1;      // [n1] threshold bin of list-1 position (or kNoSlot)
     const uint16_t *bin2;      // [n2]
     const int32_t *slot2_of_1; // [n1]
+    const uint32_t *rowstart_bits;  // [n1/32 + 2] bit p set iff list-1 position p starts a new threshold row (bin1[p] != bin1[p-1])
     double level_log[kMaxLevels + 1];  // log tau_l ; [0] = +inf
 };
 

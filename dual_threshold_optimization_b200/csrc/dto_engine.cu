@@ -95,7 +95,7 @@ struct dto_b200_ctx {
     bool has_problem = false;
     Problem P{};
     // problem tables
-    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts;
+    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts, d_rowbits;
     // batch state
     DevBuf d_pb, d_records, d_status, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
         d_err, d_pair, d_minp, d_tstats, d_words;
@@ -263,7 +263,7 @@ void dto_b200_destroy(dto_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_c1, &ctx->d_c2, &ctx->d_thr1, &ctx->d_thr2, &ctx->d_lf, &ctx->d_rowA, &ctx->d_colB,
-                      &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
+                      &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_rowbits, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
                       &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_H,
                       &ctx->d_pv, &ctx->d_logp, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_err, &ctx->d_pair,
                       &ctx->d_minp, &ctx->d_tstats, &ctx->d_words};
@@ -394,10 +394,12 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.n1_eff = c1[T1 - 1];
     P.never = (ctx->opt_swar && c1[T1 - 1] <= 32766u && c2[T2 - 1] <= 32766u) ? 0x7FFFu : 0xFFFFu;
     P.pb_stride = ((P.n1_eff + 1 + 255) / 256) * 256;  // whole staging chunks (cp.async in the scan), 512 B aligned rows
-    std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(n2 ? n2 : 1);
+    std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(((n2 ? n2 : 1) + 3) & ~(size_t)3, kNoSlot);
+    std::vector<uint32_t> rowbits(n1 / 32 + 2, 0u);
     for (size_t j = 0; j < n1; ++j) {
         const size_t b = std::lower_bound(thr1, thr1 + T1, ranks1[j]) - thr1;
         bin1[j] = b < T1 ? (uint16_t)b : kNoSlot;
+        if (j > 0 && bin1[j] != bin1[j - 1]) rowbits[j >> 5] |= 1u << (j & 31);
     }
     for (size_t j = 0; j < n2; ++j) {
         const size_t b = std::lower_bound(thr2, thr2 + T2, ranks2[j]) - thr2;
@@ -431,6 +433,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     CUDA_TRY(up(ctx->d_dslot2, dslot2.data(), dslot2.size() * 2));
     CUDA_TRY(up(ctx->d_bin1, bin1.data(), bin1.size() * 2));
     CUDA_TRY(up(ctx->d_bin2, bin2.data(), bin2.size() * 2));
+    CUDA_TRY(up(ctx->d_rowbits, rowbits.data(), rowbits.size() * 4));
     CUDA_TRY(up(ctx->d_slot2, slot2_of_1, n1 * 4));  // n1 >= 1 here (T1 >= 1)
     CUDA_TRY(ctx->d_kcrit.ensure((size_t)(P.levels + 1) * T1 * P.T2pad * 2));
     P.c1 = ctx->d_c1.as<uint32_t>();
@@ -445,6 +448,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.bin1 = ctx->d_bin1.as<uint16_t>();
     P.bin2 = ctx->d_bin2.as<uint16_t>();
     P.slot2_of_1 = ctx->d_slot2.as<int32_t>();
+    P.rowstart_bits = ctx->d_rowbits.as<uint32_t>();
     // screen tables, then the log-p table: counts -> exclusive scan (host; a few hundred thousand words) -> fill
     const size_t cells = T1 * T2;
     CUDA_TRY(ctx->d_counts.ensure(cells * 4));

@@ -141,6 +141,7 @@ struct SortShared {
     uint16_t *arrival;   // [n]     arrival slot inside the bucket
     uint32_t *scan_tmp;  // [33]: [0..31] warp partials of the block scan, [32] = boundary-list counter
     uint32_t *list;      // [n]     (global scratch) elements of buckets that straddle a row boundary: bucket << 16 | element
+    const uint32_t *rowbits;  // [n/32 + 2] shared copy of Problem::rowstart_bits
 };
 
 __device__ __forceinline__ void philox_keys(uint32_t (&out)[4], uint64_t seed, uint64_t perm_id, uint32_t stream,
@@ -327,6 +328,9 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, uint3
     for (uint32_t c = tid; c < nblk; c += nt) {
         uint32_t key[4];
         philox_keys(key, seed, perm_id, stream, c);
+        // partner slots of the 4 elements of this key block: one 8-byte load (dslot2 is padded to a multiple of 4)
+        const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + (size_t)c * 4);
+        const uint16_t ds[4] = {(uint16_t)(dsv.x & 0xFFFFu), (uint16_t)(dsv.x >> 16), (uint16_t)(dsv.y & 0xFFFFu), (uint16_t)(dsv.y >> 16)};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t e = c * 4 + q;
@@ -334,8 +338,16 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, uint3
                 const uint32_t b = key[q] >> (32 - B);
                 const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
                 const uint32_t pos = lo + S.arrival[e];
-                if (P.bin1[lo] == P.bin1[hi - 1]) {
-                    if (pos < P.n1_eff) stage[pos] = P.dslot2[e];
+                // single-row bucket <=> no row starts at positions lo+1 .. hi-1 (bitmap window of <= 32 bits)
+                const uint32_t span = hi - lo - 1;
+                bool single = span == 0;
+                if (!single && span <= 32) {
+                    const uint32_t w = (lo + 1) >> 5, sh = (lo + 1) & 31;
+                    const uint32_t win = __funnelshift_r(S.rowbits[w], S.rowbits[w + 1], sh);
+                    single = (win & (span == 32 ? 0xFFFFFFFFu : ((1u << span) - 1u))) == 0;
+                }
+                if (single) {
+                    if (pos < P.n1_eff) stage[pos] = ds[q];
                 } else {
                     S.words[pos] = (((key[q] >> (16 - B)) & 0xFFFFu) << 16) | e;
                     S.list[atomicAdd(&S.scan_tmp[32], 1u)] = (b << 16) | e;
@@ -382,8 +394,13 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
     uint16_t *order2 = S.arrival + ((nmax + 3) & ~3u);
     uint16_t *after = order2 + (identical ? 0u : ((P.n_common + 3) & ~3u));
-    S.words = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax : reinterpret_cast<uint32_t *>(after);
+    S.words = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax
+                            : reinterpret_cast<uint32_t *>(after) + (P.n1 / 32 + 2);
     S.list = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax + nmax : nullptr;
+    uint32_t *rowbits = reinterpret_cast<uint32_t *>(after);  // [n1/32 + 2]
+    S.rowbits = rowbits;
+    for (uint32_t x = threadIdx.x; x < P.n1 / 32 + 2; x += blockDim.x) rowbits[x] = P.rowstart_bits[x];
+    __syncthreads();
     const bool rowwise = identical && pairing_out == nullptr && words_scratch != nullptr;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
 
@@ -1126,6 +1143,7 @@ size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem) {
     b += (size_t)((nmax + 3) & ~3u) * 2;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
     if (!identical) b += (size_t)((P.n_common + 3) & ~3u) * 2;
+    b += (size_t)(P.n1 / 32 + 2) * 4;
     if (words_in_smem) b += (size_t)nmax * 4;
     return (b + 15) & ~(size_t)15;
 }
