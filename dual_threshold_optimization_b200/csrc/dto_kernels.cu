@@ -496,8 +496,7 @@ struct __align__(16) Cand {
 template <int CH>
 struct ScanLayout {
     static constexpr int CHP = CH + 2;           // even (64-bit column pairs) and CHP/2 odd for CH % 4 == 0
-    static constexpr int HALF = 2 * ((CH / 2 + 1) / 2);  // the screen loop checks the queue after HALF columns
-    static constexpr int QCAP = 32 * HALF + 64;  // < 32 left-overs + one half row, rounded up
+    static constexpr int QCAP = 32 * CH + 32;    // < 32 left-overs + one full row
     static constexpr int CAP = kCandCap;
     static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
     static constexpr size_t q_bytes = ((size_t)QCAP * 6 + 15) & ~(size_t)15;  // u32 (row<<16|col) + u16 k per entry
@@ -905,7 +904,7 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
             }
             koff += inc - run;
             const uint32_t koff2 = koff * 0x10001u;
-            // (3) screen: only k >= kcrit can have p <= tau_level.  Two halves so the queue only needs half a row.
+            // (3) screen: only k >= kcrit can have p <= tau_level
             auto screen = [&](int q) {
                 const uint32_t kk = kcur2[q] + koff2;  // no carry between the halves: every k < 65536
                 const uint32_t k0 = kk & 0xFFFFu, k1 = kk >> 16;
@@ -920,34 +919,20 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                     Qk[slot] = (uint16_t)k1;
                 }
             };
-            constexpr int NH = (NP + 1) / 2;
             if constexpr (SWAR) {
                 // packed 15-bit compare, branch-free: field = k + 0x8000 - kcrit keeps its top bit iff k >= kcrit (all
-                // values < 0x8000, "never" = 0x7FFF, so no borrow crosses the fields); one test per half row
+                // values < 0x8000, "never" = 0x7FFF, so no borrow crosses the fields); one test per row
                 const uint32_t bias = koff2 + 0x80008000u;
                 uint32_t hit = 0;
 #pragma unroll
-                for (int q = 0; q < NH; ++q) hit |= (kcur2[q] + bias - kc2[q]);
+                for (int q = 0; q < NP; ++q) hit |= (kcur2[q] + bias - kc2[q]);
                 if (hit & 0x80008000u) {
 #pragma unroll
-                    for (int q = 0; q < NH; ++q) screen(q);
-                }
-                __syncwarp();
-                if (*qcnt >= 32) level = drain_queue(P, R, false, level);
-                hit = 0;
-#pragma unroll
-                for (int q = NH; q < NP; ++q) hit |= (kcur2[q] + bias - kc2[q]);
-                if (hit & 0x80008000u) {
-#pragma unroll
-                    for (int q = NH; q < NP; ++q) screen(q);
+                    for (int q = 0; q < NP; ++q) screen(q);
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < NH; ++q) screen(q);
-                __syncwarp();
-                if (*qcnt >= 32) level = drain_queue(P, R, false, level);
-#pragma unroll
-                for (int q = NH; q < NP; ++q) screen(q);
+                for (int q = 0; q < NP; ++q) screen(q);
             }
             __syncwarp();
             if (*qcnt >= 32) level = drain_queue(P, R, false, level);
@@ -1085,7 +1070,7 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
 size_t scan_smem_bytes(int CH, int T1, int warps) {
     const size_t chp = (size_t)(CH + 2);
     const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
-    const size_t q = ((size_t)(32 * (2 * ((CH / 2 + 1) / 2)) + 64) * 6 + 15) & ~(size_t)15;
+    const size_t q = ((size_t)(32 * CH + 32) * 6 + 15) & ~(size_t)15;
     const size_t per = d + q + 16 + (size_t)kCandCap * sizeof(Cand) + (size_t)kRing * 2;
     return (((size_t)T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * per;
 }
