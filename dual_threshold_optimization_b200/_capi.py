@@ -127,6 +127,7 @@ SYMBOLS = {
     "dto_b200_hypergeometric_pvalues": (C.c_int, [_vp, _u64p, _u64p, _u64p, _u64p, C.c_size_t, _f64p]),
     "dto_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "dto_b200_reset_stats": (C.c_int, [_vp]),
+    "dto_b200_table_logp": (C.c_int, [_vp, _u32p, _u32p, _u32p, C.c_size_t, _f64p]),
     "dto_b200_last_batch_task_stats": (C.c_int, [_vp, _u32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dto_b200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "dto_b200_probe_fp64_tflops": (C.c_int, [_vp, _f64p]),

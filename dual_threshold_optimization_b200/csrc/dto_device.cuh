@@ -39,7 +39,6 @@ struct Problem {
     int CHP;         // CH + 2: padded stride (words) of the per-warp row histogram: even for 64-bit column pairs
     int T2pad;       // 32 * CH
     int levels;      // number of screen levels beyond level 0
-    int debug_task;  // diagnostics: task index whose refined cells are printed (-1 = off)
     uint32_t never;  // kcrit value meaning "no overlap passes": 0x7FFF when every set size is <= 32766 (packed 15-bit
                      // screen), else 0xFFFF
     uint32_t n1, n2;

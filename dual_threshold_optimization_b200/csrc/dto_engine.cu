@@ -100,7 +100,6 @@ struct dto_b200_ctx {
     DevBuf d_pb, d_records, d_status, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
         d_err, d_pair, d_minp, d_tstats, d_words;
     bool opt_task_stats = false;
-    int opt_debug_task = -1;
     bool opt_swar = true;
     int last_batch_n = 0;
     PinnedBuf h_records, h_status, h_stage;
@@ -286,9 +285,6 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
     } else if (s == "warps_per_cta") {
         if (value < 1 || value > kScanThreads / 32) return fail(DTO_B200_ERR_INVALID, "warps_per_cta out of range");
         ctx->opt_warps = (int)value;
-    } else if (s == "debug_task") {
-        ctx->opt_debug_task = (int)value;
-        ctx->P.debug_task = (int)value;
     } else if (s == "packed_screen") {
         if (ctx->has_problem) return fail(DTO_B200_ERR_STATE, "set 'packed_screen' before dto_b200_set_problem");
         ctx->opt_swar = value != 0;
@@ -322,6 +318,25 @@ int dto_b200_last_batch_task_stats(dto_b200_ctx *ctx, uint32_t *out, size_t max_
     const size_t n = std::min(max_tasks, (size_t)ctx->last_batch_n);
     CUDA_TRY(cudaMemcpy(out, ctx->d_tstats.p, n * 4 * kTaskStatWords, cudaMemcpyDeviceToHost));
     *n_out = n;
+    return DTO_B200_OK;
+}
+
+int dto_b200_table_logp(dto_b200_ctx *ctx, const uint32_t *row, const uint32_t *col, const uint32_t *k, size_t count,
+                        double *logp_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if (count == 0) return DTO_B200_OK;
+    if (!row || !col || !k || !logp_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    const Problem &P = ctx->P;
+    for (size_t x = 0; x < count; ++x) {
+        logp_out[x] = NAN;
+        if (row[x] >= (uint32_t)P.T1 || col[x] >= (uint32_t)P.T2) return fail(DTO_B200_ERR_INVALID, "cell %zu out of range", x);
+        uint2 meta;
+        CUDA_TRY(cudaMemcpy(&meta, P.cellmeta + (size_t)row[x] * P.T2 + col[x], sizeof(meta), cudaMemcpyDeviceToHost));
+        const uint32_t kbase = meta.y & 0xFFFFu, cnt = meta.y >> 16;
+        if (k[x] >= kbase && k[x] - kbase < cnt)
+            CUDA_TRY(cudaMemcpy(&logp_out[x], P.lptab + meta.x + (k[x] - kbase), sizeof(double), cudaMemcpyDeviceToHost));
+    }
     return DTO_B200_OK;
 }
 
@@ -378,7 +393,6 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.CHP = P.CH + 2;
     P.T2pad = 32 * P.CH;
     P.levels = ctx->opt_levels;
-    P.debug_task = ctx->opt_debug_task;
     P.n1 = (uint32_t)n1;
     P.n2 = (uint32_t)n2;
     P.N = population;

@@ -13,8 +13,6 @@
 //                              also the last-resort path for degenerate tasks (min p >= 1)
 #include "dto_kernels.cuh"
 
-#include <cstdio>
-
 namespace dto {
 
 // =====================================================================================================

@@ -148,6 +148,14 @@ class Engine:
         capi.check(capi.lib().dto_b200_last_batch_task_stats(self._ctx, capi.ptr(out, C.c_uint32), max_tasks, C.byref(n)))
         return out[: n.value]
 
+    def table_logp(self, rows, cols, ks) -> np.ndarray:
+        """Entries of the device log-p lookup table (NaN outside a cell's tabulated range) -- diagnostics."""
+        r, c, k = capi.u32(rows), capi.u32(cols), capi.u32(ks)
+        out = np.zeros(r.size, dtype=np.float64)
+        capi.check(capi.lib().dto_b200_table_logp(self._ctx, capi.ptr(r, C.c_uint32), capi.ptr(c, C.c_uint32),
+                                                  capi.ptr(k, C.c_uint32), r.size, capi.ptr(out, C.c_double)))
+        return out
+
     def reset_stats(self):
         capi.check(capi.lib().dto_b200_reset_stats(self._ctx))
 

@@ -137,7 +137,13 @@ int dto_b200_reset_stats(dto_b200_ctx *ctx);
  * launch; needs option "task_stats" = 1.  out holds 8 u32 per task. */
 int dto_b200_last_batch_task_stats(dto_b200_ctx *ctx, uint32_t *out, size_t max_tasks, size_t *n_out);
 
-/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" (before set_problem), "task_stats" */
+/* diagnostics: the per-problem log-p lookup table the scan kernel reads: natural log of
+ * hypergeometric_pvalue(N, set1_len[row], set2_len[col], k) for `count` (row, col, k) triples, NaN where (k) lies outside
+ * the tabulated range of that cell.  Lets a checker bound the table's error against the oracle. */
+int dto_b200_table_logp(dto_b200_ctx *ctx, const uint32_t *row, const uint32_t *col, const uint32_t *k, size_t count,
+                        double *logp_out);
+
+/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" and "packed_screen" (before set_problem), "task_stats" */
 int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value);
 
 /* micro-probes used by bench.py for roofline denominators (measured live, not assumed) */

@@ -478,3 +478,30 @@ def test_huge_rank_values_many_thresholds(engine):
             H.assert_record_matches(recs[t], O.grid_int(o1, o2, N, slot, p1[t], p2[t], want_overlap=False, want_p=False).best)
     ph = engine.run_permuted_philox(1, 0, 50)
     assert np.all((ph["pvalue"] > 0) & (ph["pvalue"] <= 1.0))
+
+
+def test_lookup_table_accuracy(engine):
+    """The scan kernel trusts the per-problem log-p table to ~1e-8 when it shortlists candidates for the exact stage:
+    bound its error against the oracle's log-sum-exp on random cells of the N = 20 000 problem."""
+    N = 20000
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, N, 0.25)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    lf = O.ln_factorial_table(pop)
+    c1 = np.searchsorted(o1.ranks, o1.thresholds, side="right")
+    c2 = np.searchsorted(o2.ranks, o2.thresholds, side="right")
+    rng = np.random.default_rng(3)
+    rows = rng.integers(0, 589, size=4000)
+    cols = rng.integers(0, 589, size=4000)
+    K, n = c1[rows], c2[cols]
+    mean = K * n / N
+    sd = np.sqrt(np.maximum(K * n * (N - K) * (N - n) / (N ** 2 * (N - 1.0)), 1e-9))
+    ks = np.clip(np.round(mean + rng.uniform(-1.0, 5.0, size=4000) * sd + rng.integers(0, 2, size=4000)), 1, np.minimum(K, n)).astype(np.int64)
+    got = engine.table_logp(rows, cols, ks)
+    inside = ~np.isnan(got)
+    assert inside.sum() > 1500
+    worst = 0.0
+    for x in np.nonzero(inside)[0]:
+        want = O.hypergeometric_log_pvalue(lf, pop, int(K[x]), int(n[x]), int(ks[x]))
+        worst = max(worst, abs(got[x] - want))
+        assert np.log(1.5e-5) - 1e-3 <= want <= np.log(0.95) + 1e-3  # the tabulated range is tau_32 .. tau_1
+    assert worst < 1e-9, worst

@@ -12,8 +12,6 @@ l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2
 eng = dto.Engine(0)
 eng.set_option("task_stats", 1)
 eng.set_option("batch", P)
-if len(sys.argv) > 3:
-    eng.set_option("debug_task", int(sys.argv[3]))
 eng.load_lists(l1, l2, N)
 rec = eng.run_permuted_philox(1, 0, P)
 ts = eng.last_batch_task_stats(P).astype(np.float64)
@@ -26,10 +24,6 @@ out["sum_cycles_over_warps"] = float(cyc.sum())
 worst = np.argsort(-cyc)[:5]
 out["worst"] = [{"task": int(t), "cycles": float(cyc[t]), "screened": int(ts[t, 0]), "refined": int(ts[t, 1]), "minp": float(rec[t]["pvalue"]),
                  "rank1": int(rec[t]["rank1"]), "rank2": int(rec[t]["rank2"]),
-                 "cyc_scatter": float(ts[t, 4] * 16), "cyc_drain": float(ts[t, 5] * 16), "cyc_refine": float(ts[t, 6] * 16), "cyc_exact": float(ts[t, 7] * 16)} for t in worst]
-med = np.argsort(cyc)[len(cyc) // 2]
-out["median_task"] = {"cycles": float(cyc[med]), "screened": int(ts[med, 0]), "cyc_scatter": float(ts[med, 4] * 16), "cyc_drain": float(ts[med, 5] * 16),
-                      "cyc_refine": float(ts[med, 6] * 16), "cyc_exact": float(ts[med, 7] * 16)}
-out["mean_phase_cycles"] = {"scatter": float(ts[:, 4].mean() * 16), "drain": float(ts[:, 5].mean() * 16), "refine": float(ts[:, 6].mean() * 16), "exact": float(ts[:, 7].mean() * 16)}
+                 "final_level": int(ts[t, 4])} for t in worst]
 out["lptab_entries"] = eng.stats()["lptab_entries"]
 print(json.dumps(out, indent=1))
