@@ -570,11 +570,11 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
     // The sort buffer + boundary list of the pairing kernel live in a per-CTA global scratch (2 x nmax words, L2-
     // resident): the row-wise fast path touches it for ~4 % of the elements only, and long lists would not fit it in
     // shared memory anyway.
-    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
+    if (sigma_smem_bytes(P, B1, B2, false, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel needs %zu B of shared memory (> %zu)",
-                    sigma_smem_bytes(P, B1, B2, false), ctx->smem_optin);
+                    sigma_smem_bytes(P, B1, B2, false, false), ctx->smem_optin);
     const int sigma_grid_max = ctx->sm_count * 4;
-    CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * 2 * std::max(P.n1, P.n2) * 4));
+    CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * 3 * std::max(P.n1, P.n2) * 4));
     uint32_t *words_scratch = ctx->d_words.as<uint32_t>();
     const size_t batch = (size_t)auto_batch(ctx);
     ctx->stats.last_scan_kernel_ms = 0;
@@ -597,7 +597,7 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
         CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
         CUDA_TRY(launch_sigma_sort(P, seed, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr, words_scratch,
-                                   std::min(n, sigma_grid_max), ctx->stream));
+                                   ctx->smem_optin, std::min(n, sigma_grid_max), ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
         ctx->stats.kernel_launches += 1;
         rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
@@ -646,14 +646,15 @@ int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, 
     if (!pos2_of_pos1_out) return fail(DTO_B200_ERR_INVALID, "null output");
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
+    if (sigma_smem_bytes(P, B1, B2, false, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel does not fit shared memory");
-    CUDA_TRY(ctx->d_words.ensure((size_t)2 * std::max(P.n1, P.n2) * 4));
+    CUDA_TRY(ctx->d_words.ensure((size_t)3 * std::max(P.n1, P.n2) * 4));
     uint32_t *words_scratch = ctx->d_words.as<uint32_t>();
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
     CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_pair.p, 0xFF, (size_t)(P.n1 ? P.n1 : 1) * 4, ctx->stream));
-    CUDA_TRY(launch_sigma_sort(P, seed, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), words_scratch, 1, ctx->stream));
+    CUDA_TRY(launch_sigma_sort(P, seed, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), words_scratch,
+                               ctx->smem_optin, 1, ctx->stream));
     ctx->stats.kernel_launches += 1;
     CUDA_TRY(cudaMemcpyAsync(pos2_of_pos1_out, ctx->d_pair.p, (size_t)P.n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

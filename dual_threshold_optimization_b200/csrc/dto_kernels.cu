@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
                                                                    uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
                                                                    uint32_t *__restrict__ pairing_out,
-                                                                   uint32_t *__restrict__ words_scratch) {
+                                                                   uint32_t *__restrict__ words_scratch,
+                                                                   int arrival_in_scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
@@ -388,13 +389,15 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     S.scan_tmp = S.cnt + (1u << Bmax) + 1;
     const uint32_t stage_len = P.pb_stride;
     uint16_t *stage = reinterpret_cast<uint16_t *>(S.scan_tmp + 33);  // (NB + 1 + 33) words: 8-byte aligned for B >= 1
-    S.arrival = stage + stage_len;                                    // pb_stride is a multiple of 256
+    // per-CTA global scratch: words[nmax] | list[nmax] | arrival[nmax] (u16, only when it does not fit shared memory)
+    uint32_t *scratch = words_scratch ? words_scratch + (size_t)blockIdx.x * 3 * nmax : nullptr;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
-    uint16_t *order2 = S.arrival + ((nmax + 3) & ~3u);
+    uint16_t *arr_smem = stage + stage_len;  // pb_stride is a multiple of 256
+    S.arrival = arrival_in_scratch ? reinterpret_cast<uint16_t *>(scratch + 2 * (size_t)nmax) : arr_smem;
+    uint16_t *order2 = arr_smem + (arrival_in_scratch ? 0u : ((nmax + 3) & ~3u));
     uint16_t *after = order2 + (identical ? 0u : ((P.n_common + 3) & ~3u));
-    S.words = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax
-                            : reinterpret_cast<uint32_t *>(after) + (P.n1 / 32 + 2);
-    S.list = words_scratch ? words_scratch + (size_t)blockIdx.x * 2 * nmax + nmax : nullptr;
+    S.words = scratch ? scratch : reinterpret_cast<uint32_t *>(after) + (P.n1 / 32 + 2);
+    S.list = scratch ? scratch + nmax : nullptr;
     uint32_t *rowbits = reinterpret_cast<uint32_t *>(after);  // [n1/32 + 2]
     S.rowbits = rowbits;
     for (uint32_t x = threadIdx.x; x < P.n1 / 32 + 2; x += blockDim.x) rowbits[x] = P.rowstart_bits[x];
@@ -1052,6 +1055,13 @@ __global__ void hbm_copy_probe_kernel(const uint4 *__restrict__ src, uint4 *__re
 // =====================================================================================================
 // launchers
 // =====================================================================================================
+static int max_optin_smem() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return v;
+}
+
 template <int CH, bool SWAR>
 static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags,
                                  dto_b200_record *out, uint32_t *status, unsigned long long *counters,
@@ -1059,7 +1069,9 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
     using L = ScanLayout<CH>;
     const size_t smem = (((size_t)P.T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * L::per_warp;
     auto kern = scan_kernel<CH, SWAR>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // always the device maximum: the attribute is per function and process-wide, and several contexts (host threads)
+    // may launch the same instantiation with different sizes concurrently
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, st>>>(P, pb, n_tasks, flags, out, status, counters, task_stats);
     return cudaGetLastError();
@@ -1118,12 +1130,12 @@ cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *
 }
 
 // shared-memory bytes of the pairing kernel; words_in_smem = false moves the n x 4 B sort buffer to a global scratch
-size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem) {
+size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem, bool arrival_in_smem) {
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
     size_t b = ((size_t)(1u << Bmax) + 1 + 33) * 4;
     b += (size_t)P.pb_stride * 2;
-    b += (size_t)((nmax + 3) & ~3u) * 2;
+    if (arrival_in_smem) b += (size_t)((nmax + 3) & ~3u) * 2;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
     if (!identical) b += (size_t)((P.n_common + 3) & ~3u) * 2;
     b += (size_t)(P.n1 / 32 + 2) * 4;
@@ -1141,12 +1153,16 @@ int pick_bucket_bits(uint32_t n) {
 }
 
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
-                              uint32_t *pairing_out, uint32_t *words_scratch, int grid, cudaStream_t st) {
+                              uint32_t *pairing_out, uint32_t *words_scratch, size_t smem_limit, int grid,
+                              cudaStream_t st) {
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    const size_t smem = sigma_smem_bytes(P, B1, B2, words_scratch == nullptr);
-    cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool arrival_in_smem = sigma_smem_bytes(P, B1, B2, false, true) <= smem_limit;
+    const size_t smem = sigma_smem_bytes(P, B1, B2, false, arrival_in_smem);
+    if (smem > smem_limit || !words_scratch) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
-    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, words_scratch);
+    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, words_scratch,
+                                                        arrival_in_smem ? 0 : 1);
     return cudaGetLastError();
 }
 

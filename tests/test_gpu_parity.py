@@ -418,6 +418,9 @@ def test_batched_pairs_driver(engine):
     # null pairs: the empirical p of a null pair is roughly uniform -- at least not all tiny
     assert max(a[q]["empirical_pvalue"] for q in (0, 2, 4)) > 0.05
     assert dto.run_pairs(pairs, 400, seed=10) != a
+    # concurrency stress: four contexts on one GPU working on problems of different shapes at the same time
+    for rep in range(3):
+        assert dto.run_pairs(pairs * 3, 150, devices=[0, 0, 0, 0], seed=rep) == dto.run_pairs(pairs * 3, 150, devices=[0], seed=rep)
 
 
 def test_generic_and_packed_screen_agree(engine, built):
@@ -438,13 +441,13 @@ def test_generic_and_packed_screen_agree(engine, built):
     H.assert_record_matches(u, O.grid_int(o1, o2, 3000).best)
 
 
-def test_long_lists_generic_path(engine):
-    """40 000-feature lists (> 32 766: generic screen, sort buffer in the global scratch): a few permutations replayed
-    through the oracle."""
-    N = 40000
+@pytest.mark.parametrize("N,T", [(40000, 659), (65534, 708)])
+def test_long_lists_generic_path(engine, N, T):
+    """Lists longer than 32 766 features (generic 16-bit screen; at the 65 534-feature maximum the pairing kernel also
+    moves its arrival slots to the global scratch): a few permutations replayed through the oracle."""
     ids1, r1, ids2, r2 = H.synthetic_pair(N, 4, None)
     o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
-    assert engine.shape[:2] == (659, 659)
+    assert engine.shape[:2] == (T, T)
     lf = O.ln_factorial_table(pop)
     recs = engine.run_permuted_philox(3, 0, 64)
     for t in (0, 63):
