@@ -708,6 +708,7 @@ __device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, i
         R.n_level2 += take;
         qc = start;
     }
+    __syncwarp();  // every lane has read the old count before lane 0 replaces it
     if (lane == 0) *R.qcnt = qc;
     __syncwarp();
     while (level < P.levels && R.theta <= P.level_log[level + 1]) ++level;
