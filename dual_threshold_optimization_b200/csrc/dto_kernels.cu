@@ -861,7 +861,11 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         issue_chunk(2);
         uint32_t cbase = 0, lo = 0;
         uint2 *D2 = reinterpret_cast<uint2 *>(D + lane * CHP);  // this lane's column pairs (8-byte aligned: CHP even)
-        for (int i = 0; i < P.T1; ++i) {
+        // The row loop is call-free: when the queue holds a full chunk it BREAKS to the (out-of-line) drain and
+        // re-enters, so the column state is only saved/restored around that rare call, never inside the loop.
+        int i = 0;
+        while (i < P.T1) {
+        for (; i < P.T1; ++i) {
             const uint32_t hi = s_c1[i];
             // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
             // the scatter)
@@ -937,7 +941,12 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 for (int q = 0; q < NP; ++q) screen(q);
             }
             __syncwarp();
-            if (*qcnt >= 32) level = drain_queue(P, R, false, level);
+            if (*qcnt >= 32) {
+                ++i;
+                break;
+            }
+        }
+        if (i < P.T1 || *qcnt >= 32) level = drain_queue(P, R, false, level);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         finish_task(P, R, task, level, record_flags, out, status, counters, task_stats, t_begin);
