@@ -55,7 +55,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -332,6 +332,11 @@ def main():
                     "binding_resource": "warp instruction issue / fixed-latency dependencies at 16 warps per SM (register-limited)",
                     "ncu": ncu, "ncu_note": "static figures of one captured launch (profiles/scan_kernel_ncu_latest.json), not measured in this run",
                 },
+                "issue_view": (None if not ncu else {
+                    "achieved_warp_inst_per_s": ncu["warp_instructions_per_permutation"] * perms_per_launch / (avg_launch_ms * 1e-3),
+                    "peak_warp_inst_per_s": 148 * 4 * (clk["sm_mhz"] or 1965.0) * 1e6,
+                    "frac": ncu["warp_instructions_per_permutation"] * perms_per_launch / (avg_launch_ms * 1e-3) / (148 * 4 * (clk["sm_mhz"] or 1965.0) * 1e6),
+                    "note": "warp instructions per permutation (ncu, static) x live permutation rate of the kernel vs 148 SMs x 4 schedulers x SM clock"}),
                 "hbm_view": {"achieved_gbs": hbm_bytes_per_perm * perms_per_launch / (avg_launch_ms * 1e-3) / 1e9,
                              "peak_gbs": peaks.get("hbm_gbs"), "frac": hbm_bytes_per_perm * perms_per_launch / (avg_launch_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", float("nan")),
                              "note": "algorithmic HBM bytes/permutation of the scan kernel = one partner-slot row read (2 B x padded n1) + one 40 B record"},

@@ -130,7 +130,7 @@ int auto_batch(const dto_b200_ctx *ctx) {
 }
 
 // Runs the scan over n tasks whose partner-slot rows are already in ctx->d_pb; results land in
-// ctx->d_records[0..n).  Escalates overflowed tasks to the wide kernel and degenerate ones to the dense path.
+// ctx->d_records[0..n).  Degenerate tasks (minimum p >= 1: no cell beats the short-circuited ones) go to the dense path.
 int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags) {
     const Problem &P = ctx->P;
     CUDA_TRY(ctx->d_records.ensure((size_t)n * sizeof(dto_b200_record)));

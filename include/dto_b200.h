@@ -87,8 +87,8 @@ int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, cons
                                   dto_b200_record *records_out);
 
 /* P tasks with ON-DEVICE permutations: task p uses permutation id first_perm_id + p, whose pairing is a
- * Philox4x32-10-keyed bijection of the sorted positions (DESIGN.md "permutation generator"); results do
- * not depend on batching or on how ids are sharded over GPUs.  Either output may be NULL. HOST buffers. */
+ * uniform random permutation obtained by sorting Philox4x32-10 keys (counter = element, stream, id; key = seed;
+ * DESIGN.md section 4, K0); results do not depend on batching or on how ids are sharded over GPUs.  Either output may be NULL. HOST buffers. */
 int dto_b200_run_permuted_philox(dto_b200_ctx *ctx, uint64_t seed, uint64_t first_perm_id, size_t P,
                                  dto_b200_record *records_out, double *minp_out);
 

@@ -120,3 +120,40 @@ def assert_record_matches(rec, ob, rel=1e-12):
         assert p == 0.0, (p, q)
     else:
         assert abs(p - q) <= rel * abs(q), (p, q)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Philox4x32-10 (Salmon et al. SC'11) in numpy: an independent restatement used to replay the device generator
+# ---------------------------------------------------------------------------------------------------
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = [np.asarray(x, dtype=np.uint64) for x in (c0, c1, c2, c3)]
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ np.uint64(k0)) & MASK, p1 & MASK, ((p0 >> np.uint64(32)) ^ c3 ^ np.uint64(k1)) & MASK, p0 & MASK
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def device_keys(n, seed, perm_id, stream):
+    """The 32-bit sort key of every element, as the pairing kernel derives it: counter = (element / 4, stream, id lo, id hi),
+    key = (seed lo, seed hi), word element % 4."""
+    blk = np.arange((n + 3) // 4, dtype=np.uint64)
+    out = philox4x32_10(blk, np.full_like(blk, stream), np.full_like(blk, perm_id & 0xFFFFFFFF), np.full_like(blk, perm_id >> 32),
+                        seed & 0xFFFFFFFF, seed >> 32)
+    return np.stack(out, axis=1).reshape(-1)[:n]
+
+
+def expected_pairing_identical(n, seed, perm_id):
+    """pos2_of_pos1 for identical gene sets: list-1 position f is paired with the list-2 position whose key has rank f.
+    Order = (top B + 16 key bits, secondary Philox key (stream + 8), index), B = bucket bits of the kernel."""
+    lg = 0
+    while (1 << lg) < n:
+        lg += 1
+    B = min(14, max(1, lg - 1))
+    key = device_keys(n, seed, perm_id, 0)
+    sec = device_keys(n, seed, perm_id, 8)
+    primary = key >> np.uint64(16 - B)
+    order = np.lexsort((np.arange(n), sec, primary))
+    return order.astype(np.uint32)

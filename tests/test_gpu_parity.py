@@ -508,3 +508,14 @@ def test_lookup_table_accuracy(engine):
         worst = max(worst, abs(got[x] - want))
         assert np.log(1.5e-5) - 1e-3 <= want <= np.log(0.95) + 1e-3  # the tabulated range is tau_32 .. tau_1
     assert worst < 1e-9, worst
+
+
+@pytest.mark.parametrize("n", [30, 1000, 6000, 20000])
+def test_device_generator_is_philox_sort(engine, n):
+    """The exported device permutation equals an independent numpy replay: Philox4x32-10 keys sorted on (key bits,
+    secondary key, index).  This pins both the Philox implementation and the shared-memory sort."""
+    ids1, r1, ids2, r2 = H.synthetic_pair(n, 8, None)
+    load(engine, ids1, r1, ids2, r2)
+    for seed, pid in ((0, 0), (12345678901234567, 7), (2 ** 63 + 5, 2 ** 40 + 3)):
+        got = engine.philox_pairing(seed, pid)
+        assert np.array_equal(got, H.expected_pairing_identical(n, seed, pid)), (n, seed, pid)

@@ -188,3 +188,13 @@ def test_run_single_node_threads_and_modes():
     assert a[0]["permuted"] == 0 and a[0]["pvalue"] == 0.15632183908046102 and all(a[1:]["permuted"] == 1)
     out = O.final_json(a)
     assert 0.0 <= out["empirical_pvalue"] <= 1.0
+
+
+def test_numpy_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10 (the checker's restatement used to replay the device generator)."""
+    def words(*a):
+        return [int(x) for x in H.philox4x32_10(*a)]
+
+    assert words(0, 0, 0, 0, 0, 0) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert words(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert words(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, 0xA4093822, 0x299F31D0) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
