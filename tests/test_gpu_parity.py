@@ -519,3 +519,22 @@ def test_device_generator_is_philox_sort(engine, n):
     for seed, pid in ((0, 0), (12345678901234567, 7), (2 ** 63 + 5, 2 ** 40 + 3)):
         got = engine.philox_pairing(seed, pid)
         assert np.array_equal(got, H.expected_pairing_identical(n, seed, pid)), (n, seed, pid)
+
+
+def test_rowwise_fast_pairing_equals_exact_pairing_at_scale(engine):
+    """The performance path of the pairing kernel only resolves the ROW of every position (positions inside one
+    threshold row are interchangeable); its records must equal, bit for bit, those of the exactly ranked permutation
+    with the same id (exported, then fed back through the host-indices path).  N = 20 000, 48 ids."""
+    N = 20000
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, N, 0.25)
+    o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
+    fast = engine.run_permuted_philox(77, 500, 48)
+    ident = np.arange(N, dtype=np.uint32)
+    p1 = np.tile(ident, (48, 1))
+    p2 = np.empty((48, N), dtype=np.uint32)
+    for t in range(48):
+        pairing = engine.philox_pairing(77, 500 + t)  # exact path: pos2_of_pos1
+        # unpermuted list 1 (perm1 = identity): gene at slot j must sit at list-2 position pairing[j]
+        p2[t, pairing] = slot
+    exact = engine.run_permuted_indices(p1, p2)
+    assert np.array_equal(fast, exact)
