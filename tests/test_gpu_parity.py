@@ -299,6 +299,16 @@ def test_cli_end_to_end(built):
     assert out["rank1"] == 24 and out["rank2"] == 13 and out["unpermuted_intersection_size"] == 12 and out["fdr"] == 0.0
     assert '"unpermuted_pvalue": 0.15632183908046102' in r.stdout and '"fdr": 0.0' in r.stdout
     assert "Permutations: 5" in r.stderr and "threshold lists" in r.stderr and ": 900" in r.stderr
+    # -m shards over every visible GPU (the single-box replacement of the MPI mode); --seed makes the null reproducible
+    args = [cli, "-1", f"{td}/ranklist1.csv", "-2", f"{td}/ranklist2.csv", "-p", "2000", "-m", "--seed", "7"]
+    a = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    b = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and a.stdout == b.stdout and "Multi-node mode: enabled" in a.stderr
+    oa = json.loads(a.stdout)
+    assert oa["population_size"] == 30 and oa["rank1"] == 24 and 0.5 < oa["empirical_pvalue"] <= 1.0
+    # the reference's panics surface as a non-zero exit with the reference's message
+    bad = subprocess.run([cli, "-1", f"{td}/ranklist1.csv", "-2", f"{td}/background.txt"], capture_output=True, text=True, timeout=60)
+    assert bad.returncode != 0 and "Invalid format in file" in bad.stderr
 
 
 def test_committed_golden_vectors(engine):
@@ -538,3 +548,40 @@ def test_rowwise_fast_pairing_equals_exact_pairing_at_scale(engine):
         p2[t, pairing] = slot
     exact = engine.run_permuted_indices(p1, p2)
     assert np.array_equal(fast, exact)
+
+
+def test_fuzz_tiny_problems_against_faithful_oracle(engine):
+    """60 random tiny problems (1-40 features per list, ties, rank 0, partial gene overlap, arbitrary population):
+    dense grid, unpermuted optimum and a few host-index permutations against the reference-faithful oracle form."""
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for case in range(60):
+        n1, n2 = int(rng.integers(1, 41)), int(rng.integers(1, 41))
+        uni = H.ids_for(60, "z")
+        ids1 = [uni[i] for i in rng.choice(60, size=n1, replace=False)]
+        ids2 = [uni[i] for i in rng.choice(60, size=n2, replace=False)]
+        r1 = rng.integers(0, max(2, n1 + 5), size=n1).astype(np.uint32)
+        r2 = rng.integers(0, max(2, 2 * n2), size=n2).astype(np.uint32)
+        if r1.max() == 0 or r2.max() == 0:
+            continue  # max rank 0 -> no thresholds -> the reference panics (covered elsewhere)
+        pop = int(max(n1, n2) + rng.integers(0, 30))
+        l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+        engine.load_lists(l1, l2, pop)
+        o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+        f = O.process_threshold_pairs_faithful(o1, o2, pop)
+        ov, pv, _ = engine.grid_debug()
+        assert np.array_equal(ov.ravel(), f["intersection_size"]), case
+        assert np.allclose(pv.ravel(), f["pvalue"], rtol=1e-12, atol=0), case
+        fb = O.argmin_tiebreak(f)
+        H.assert_record_matches(engine.run_unpermuted(), {k: fb[k] for k in fb.dtype.names})
+        P = 6
+        p1, p2 = H.perms(n1, P, case), H.perms(n2, P, 1000 + case)
+        recs = engine.run_permuted_indices(p1, p2)
+        for t in range(P):
+            fbp = O.argmin_tiebreak(O.process_threshold_pairs_faithful(o1, o2, pop, p1[t], p2[t]))
+            if not int(recs[t]["flags"]) & dto._capi.FLAG_NEAR_TIE:
+                H.assert_record_matches(recs[t], {k: fbp[k] for k in fbp.dtype.names})
+        ph = engine.run_permuted_philox(case, 0, 8)
+        assert np.all(ph["pvalue"] <= 1.0 + 1e-12) and np.all(ph["pvalue"] >= 0.0)
+        checked += 1
+    assert checked >= 50
