@@ -268,14 +268,16 @@ def main():
     value_device_only = P * world * args.steps / (dev_ms_max * 1e-3)
 
     # ---- end-to-end through the public API with host buffers: lists up, records down, host epilogue ----
-    def e2e_step(step_idx):
-        eng.load_lists(l1, l2, population)          # H2D: ranks, thresholds, slot map, ln-factorial table
-        rec0 = eng.run_unpermuted()                  # D2H: the unpermuted record
-        recs = eng.run_permuted_philox(PHILOX_SEED, (step_idx * world + rank) * P, P)  # D2H: P records
-        allrec = np.concatenate([np.asarray([rec0], dtype=recs.dtype), recs])
-        from dual_threshold_optimization_b200.stat_operations import empirical_pvalue_struct
+    from dual_threshold_optimization_b200._capi import RECORD_DTYPE
+    from dual_threshold_optimization_b200.stat_operations import empirical_pvalue_struct
 
-        return empirical_pvalue_struct(allrec).empirical_pvalue
+    e2e_records = np.zeros(P + 1, dtype=RECORD_DTYPE)  # host result buffer of one step: [unpermuted, P permuted]
+
+    def e2e_step(step_idx):
+        eng.load_lists(l1, l2, population)          # H2D: ranks, thresholds, slot map (+ tables rebuilt on the device)
+        e2e_records[0] = eng.run_unpermuted()        # D2H: the unpermuted record
+        eng.run_permuted_philox(PHILOX_SEED, (step_idx * world + rank) * P, P, out=e2e_records[1:])  # D2H: P records
+        return empirical_pvalue_struct(e2e_records).empirical_pvalue   # host epilogue (empirical p, FDR)
 
     e2e_step(20_000)
     barrier()

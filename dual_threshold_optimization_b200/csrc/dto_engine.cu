@@ -101,6 +101,8 @@ struct dto_b200_ctx {
         d_err, d_pair, d_minp, d_tstats, d_words;
     bool opt_task_stats = false;
     bool opt_swar = true;
+    std::vector<double> lf_host;  // ln_factorial(0..lf_N): a pure function of the population, kept across problems
+    uint64_t lf_N = ~0ull;
     int last_batch_n = 0;
     PinnedBuf h_records, h_status, h_stage;
     // options
@@ -420,8 +422,12 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
         bin2[j] = b < T2 ? (uint16_t)b : kNoSlot;
         dslot2[j] = b < T2 ? (uint16_t)((b / P.CH) * P.CHP + (b % P.CH)) : kNoSlot;
     }
-    std::vector<double> lf;
-    host_fill_ln_factorial(lf, population);
+    const bool lf_cached = (ctx->lf_N == population && ctx->lf_host.size() == population + 1 && ctx->d_lf.p != nullptr);
+    if (!lf_cached) {
+        host_fill_ln_factorial(ctx->lf_host, population);
+        ctx->lf_N = ~0ull;  // set after the upload below succeeds
+    }
+    const std::vector<double> &lf = ctx->lf_host;
     std::vector<double> rowA(T1), colB(T2);
     for (size_t i = 0; i < T1; ++i) rowA[i] = lf[c1[i]] + lf[population - c1[i]];
     for (size_t j = 0; j < T2; ++j) colB[j] = lf[c2[j]] + lf[population - c2[j]] - lf[population];
@@ -441,7 +447,10 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     CUDA_TRY(up(ctx->d_c2, c2.data(), T2 * 4));
     CUDA_TRY(up(ctx->d_thr1, thr1, T1 * 4));
     CUDA_TRY(up(ctx->d_thr2, thr2, T2 * 4));
-    CUDA_TRY(up(ctx->d_lf, lf.data(), lf.size() * 8));
+    if (!lf_cached) {
+        CUDA_TRY(up(ctx->d_lf, lf.data(), lf.size() * 8));
+        ctx->lf_N = population;
+    }
     CUDA_TRY(up(ctx->d_rowA, rowA.data(), T1 * 8));
     CUDA_TRY(up(ctx->d_colB, colB.data(), T2 * 8));
     CUDA_TRY(up(ctx->d_dslot2, dslot2.data(), dslot2.size() * 2));

@@ -80,8 +80,15 @@ class Engine:
         )
         return rec
 
-    def run_permuted_philox(self, seed: int, first_perm_id: int, P: int, want_records=True, want_minp=False):
-        rec = np.zeros(P, dtype=capi.RECORD_DTYPE) if want_records else None
+    def run_permuted_philox(self, seed: int, first_perm_id: int, P: int, want_records=True, want_minp=False, out=None):
+        """P device-generated permutations.  `out` (optional): a contiguous RECORD_DTYPE array of >= P records to fill in
+        place (e.g. a slice of a larger buffer), instead of a fresh allocation."""
+        if out is not None:
+            if out.dtype != capi.RECORD_DTYPE or out.size < P or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a contiguous RECORD_DTYPE array with at least P records")
+            rec = out
+        else:
+            rec = np.zeros(P, dtype=capi.RECORD_DTYPE) if want_records else None
         mp = np.zeros(P, dtype=np.float64) if want_minp else None
         capi.check(
             capi.lib().dto_b200_run_permuted_philox(
@@ -90,9 +97,9 @@ class Engine:
                 capi.ptr(mp, C.c_double),
             )
         )
-        if want_records and want_minp:
+        if rec is not None and want_minp:
             return rec, mp
-        return rec if want_records else mp
+        return rec if rec is not None else mp
 
     def run_permuted_philox_device(self, seed: int, first_perm_id: int, P: int, d_minp_ptr: int, d_records_ptr: int = 0):
         """Outputs stay on the device (raw device pointers, e.g. torch.Tensor.data_ptr())."""
