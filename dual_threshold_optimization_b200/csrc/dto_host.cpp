@@ -8,7 +8,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <fstream>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -24,6 +26,12 @@ struct dto_b200_ranked_list {
     std::vector<std::string> ids;      // sorted by rank (stable)
     std::vector<uint32_t> ranks;       // ascending
     std::vector<uint32_t> thresholds;  // src/collections/ranked.rs:359-375
+    uint64_t uid = 0;                  // unique per created list (lists are immutable after creation)
+    // memo of the last string-id -> slot canonicalisation against another list (a pure function of the two immutable
+    // lists); guarded by a mutex because one list may be loaded into several contexts from several threads
+    mutable std::mutex memo_mu;
+    mutable uint64_t memo_partner_uid = 0;
+    mutable std::vector<int32_t> memo_slot;
 };
 
 struct dto_b200_feature_list {
@@ -31,6 +39,8 @@ struct dto_b200_feature_list {
 };
 
 namespace {
+
+std::atomic<uint64_t> g_next_list_uid{1};
 
 std::string trim_ws(const std::string &s) {
     size_t b = 0, e = s.size();
@@ -115,6 +125,7 @@ int dto_b200_ranked_list_from(const char *const *ids, const uint32_t *ranks, siz
     *out = nullptr;
     if (n && (!ids || !ranks)) return fail(DTO_B200_ERR_INVALID, "null ids/ranks");
     auto *l = new dto_b200_ranked_list();
+    l->uid = g_next_list_uid.fetch_add(1);
     // sort_genes_and_ranks (ranked.rs:527-542): stable sort_by_key on rank
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
@@ -240,19 +251,29 @@ int dto_b200_compute_population_size(const dto_b200_ranked_list *l1, const dto_b
 int dto_b200_load_lists(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2,
                         uint64_t population) {
     if (!ctx || !l1 || !l2) return fail(DTO_B200_ERR_INVALID, "null argument");
-    std::unordered_map<std::string, int32_t> pos2;
-    pos2.reserve(l2->ids.size() * 2);
-    for (size_t j = 0; j < l2->ids.size(); ++j)
-        if (!pos2.emplace(l2->ids[j], (int32_t)j).second)
-            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list", l2->ids[j].c_str());
-    std::unordered_set<std::string> seen1;
-    seen1.reserve(l1->ids.size() * 2);
-    std::vector<int32_t> slot(l1->ids.size(), -1);
-    for (size_t a = 0; a < l1->ids.size(); ++a) {
-        if (!seen1.insert(l1->ids[a]).second)
-            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list", l1->ids[a].c_str());
-        auto it = pos2.find(l1->ids[a]);
-        if (it != pos2.end()) slot[a] = it->second;
+    std::vector<int32_t> slot;
+    {
+        std::lock_guard<std::mutex> lock(l1->memo_mu);
+        if (l1->memo_partner_uid == l2->uid && l1->memo_slot.size() == l1->ids.size()) slot = l1->memo_slot;
+    }
+    if (slot.size() != l1->ids.size() || l1->ids.empty()) {
+        std::unordered_map<std::string, int32_t> pos2;
+        pos2.reserve(l2->ids.size() * 2);
+        for (size_t j = 0; j < l2->ids.size(); ++j)
+            if (!pos2.emplace(l2->ids[j], (int32_t)j).second)
+                return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list", l2->ids[j].c_str());
+        std::unordered_set<std::string> seen1;
+        seen1.reserve(l1->ids.size() * 2);
+        slot.assign(l1->ids.size(), -1);
+        for (size_t a = 0; a < l1->ids.size(); ++a) {
+            if (!seen1.insert(l1->ids[a]).second)
+                return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list", l1->ids[a].c_str());
+            auto it = pos2.find(l1->ids[a]);
+            if (it != pos2.end()) slot[a] = it->second;
+        }
+        std::lock_guard<std::mutex> lock(l1->memo_mu);
+        l1->memo_partner_uid = l2->uid;
+        l1->memo_slot = slot;
     }
     return dto_b200_set_problem(ctx, l1->ranks.data(), l1->ranks.size(), l1->thresholds.data(), l1->thresholds.size(),
                                 l2->ranks.data(), l2->ranks.size(), l2->thresholds.data(), l2->thresholds.size(),
