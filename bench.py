@@ -52,6 +52,7 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.first = 0
 
     def start(self):
         try:
@@ -65,7 +66,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """Call at the start of the timed region: only samples taken from here on are reported."""
+        self.first = len(self.rows)
+
     def stop(self):
+        time.sleep(0.06)  # let the last 50 ms sample land
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -73,11 +79,12 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows[self.first:] or self.rows[-1:]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 9:
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
@@ -234,14 +241,15 @@ def main():
             dist.all_gather_into_tensor(gathered, d_minp)  # the small NCCL all-gather of per-permutation minima
         return ms
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # started before the warm-up (nvidia-smi needs a few 100 ms to come up); marked at the timed start
     for w in range(args.warmup):
         device_step(10_000 + w)
     barrier()
     eng.reset_stats()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     barrier()
+    clocks.mark()
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
     scan_ms = 0.0
