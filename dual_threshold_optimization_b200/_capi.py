@@ -82,6 +82,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_uint64),
         ("d2h_bytes", C.c_uint64),
         ("lptab_entries", C.c_uint64),
+        ("table_cache_hits", C.c_uint64),
     ]
 
 

@@ -36,7 +36,8 @@ constexpr double kZeroHi = -745.12;
 struct Problem {
     int T1, T2;
     int CH;          // columns per lane in the scan kernel (template value actually used)
-    int CHP;         // CH + 2: padded stride (words) of the per-warp row histogram: even for 64-bit column pairs
+    int CHP;         // hist_words(CH): 32-bit words per lane of the per-warp row histogram (two 16-bit column counts per
+                     // word, padded to whole 16-byte vectors with an odd vector count so 128-bit reads are conflict-free)
     int T2pad;       // 32 * CH
     int levels;      // number of screen levels beyond level 0
     uint32_t never;  // kcrit value meaning "no overlap passes": 0x7FFF when every set size is <= 32766 (packed 15-bit
@@ -62,6 +63,25 @@ struct Problem {
     const uint32_t *rowstart_bits;  // [n1/32 + 2] bit p set iff list-1 position p starts a new threshold row (bin1[p] != bin1[p-1])
     double level_log[kMaxLevels + 1];  // log tau_l ; [0] = +inf
 };
+
+// Row histogram of the scan kernel: lane = j / CH owns columns m = j % CH; columns (2q, 2q+1) of a lane share the
+// 32-bit word q of that lane (low / high half).  hist_words = words per lane: CH/2 rounded up to whole uint4 vectors,
+// and to an ODD number of vectors so that the 8 lanes of one 128-bit shared-memory wavefront cover all 32 banks.
+__host__ __device__ constexpr int hist_words(int CH) {
+    int v = (CH / 2 + 3) / 4;
+    if (v % 2 == 0) ++v;
+    return 4 * v;
+}
+// Histogram slot of column j as carried in the partner-slot rows: (byte offset of the word) | half, i.e.
+// (word index << 2) | (j & 1); at most 32 * 36 words, so it fits 16 bits and never equals kNoSlot.
+__host__ __device__ inline uint32_t hist_slot(int j, int CH) {
+    const int lane = j / CH, m = j % CH;
+    return ((uint32_t)(lane * hist_words(CH) + (m >> 1)) << 2) | (uint32_t)(m & 1);
+}
+__host__ __device__ inline uint32_t hist_slot_column(uint32_t slot, int CH) {
+    const uint32_t word = slot >> 2, W = (uint32_t)hist_words(CH);
+    return (word / W) * (uint32_t)CH + 2u * (word % W) + (slot & 1u);
+}
 
 // Position of column j inside a kcrit row: lane = j / CH owns columns m = j % CH; its pair m/2 is one 32-bit word and
 // the words of pair q are contiguous across lanes, so a warp reads a row with CH/2 coalesced 128-byte loads.

@@ -101,8 +101,16 @@ struct dto_b200_ctx {
         d_err, d_pair, d_minp, d_tstats, d_words;
     bool opt_task_stats = false;
     bool opt_swar = true;
+    bool opt_table_cache = true;
     std::vector<double> lf_host;  // ln_factorial(0..lf_N): a pure function of the population, kept across problems
     uint64_t lf_N = ~0ull;
+    // The screen and log-p tables are a pure function of (population, set sizes per threshold, levels, packing): list
+    // pairs that share them (e.g. tie-free ranks 1..n of equal length, config 4) reuse the tables of the previous problem.
+    bool tab_valid = false;
+    uint64_t tab_N = 0, tab_entries = 0;
+    int tab_levels = 0;
+    uint32_t tab_never = 0;
+    std::vector<uint32_t> tab_c1, tab_c2;
     int last_batch_n = 0;
     PinnedBuf h_records, h_status, h_stage;
     // options
@@ -290,6 +298,8 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
     } else if (s == "packed_screen") {
         if (ctx->has_problem) return fail(DTO_B200_ERR_STATE, "set 'packed_screen' before dto_b200_set_problem");
         ctx->opt_swar = value != 0;
+    } else if (s == "table_cache") {
+        ctx->opt_table_cache = value != 0;
     } else if (s == "task_stats") {
         ctx->opt_task_stats = value != 0;
     } else if (s == "levels") {
@@ -392,7 +402,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.T1 = (int)T1;
     P.T2 = (int)T2;
     P.CH = pick_ch((int)T2);
-    P.CHP = P.CH + 2;
+    P.CHP = hist_words(P.CH);
     P.T2pad = 32 * P.CH;
     P.levels = ctx->opt_levels;
     P.n1 = (uint32_t)n1;
@@ -420,7 +430,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     for (size_t j = 0; j < n2; ++j) {
         const size_t b = std::lower_bound(thr2, thr2 + T2, ranks2[j]) - thr2;
         bin2[j] = b < T2 ? (uint16_t)b : kNoSlot;
-        dslot2[j] = b < T2 ? (uint16_t)((b / P.CH) * P.CHP + (b % P.CH)) : kNoSlot;
+        dslot2[j] = b < T2 ? (uint16_t)hist_slot((int)b, P.CH) : kNoSlot;
     }
     const bool lf_cached = (ctx->lf_N == population && ctx->lf_host.size() == population + 1 && ctx->d_lf.p != nullptr);
     if (!lf_cached) {
@@ -443,16 +453,22 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
         ctx->stats.h2d_bytes += bytes;
         return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
-    CUDA_TRY(up(ctx->d_c1, c1.data(), T1 * 4));
-    CUDA_TRY(up(ctx->d_c2, c2.data(), T2 * 4));
+    const bool tables_cached = ctx->opt_table_cache && ctx->tab_valid && ctx->tab_N == population &&
+                               ctx->tab_levels == P.levels && ctx->tab_never == P.never && ctx->tab_c1 == c1 &&
+                               ctx->tab_c2 == c2;
+    if (!tables_cached) {
+        ctx->tab_valid = false;
+        CUDA_TRY(up(ctx->d_c1, c1.data(), T1 * 4));
+        CUDA_TRY(up(ctx->d_c2, c2.data(), T2 * 4));
+        CUDA_TRY(up(ctx->d_rowA, rowA.data(), T1 * 8));
+        CUDA_TRY(up(ctx->d_colB, colB.data(), T2 * 8));
+    }
     CUDA_TRY(up(ctx->d_thr1, thr1, T1 * 4));
     CUDA_TRY(up(ctx->d_thr2, thr2, T2 * 4));
     if (!lf_cached) {
         CUDA_TRY(up(ctx->d_lf, lf.data(), lf.size() * 8));
         ctx->lf_N = population;
     }
-    CUDA_TRY(up(ctx->d_rowA, rowA.data(), T1 * 8));
-    CUDA_TRY(up(ctx->d_colB, colB.data(), T2 * 8));
     CUDA_TRY(up(ctx->d_dslot2, dslot2.data(), dslot2.size() * 2));
     CUDA_TRY(up(ctx->d_bin1, bin1.data(), bin1.size() * 2));
     CUDA_TRY(up(ctx->d_bin2, bin2.data(), bin2.size() * 2));
@@ -472,6 +488,16 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.bin2 = ctx->d_bin2.as<uint16_t>();
     P.slot2_of_1 = ctx->d_slot2.as<int32_t>();
     P.rowstart_bits = ctx->d_rowbits.as<uint32_t>();
+    P.cellmeta = ctx->d_meta.as<uint2>();
+    P.lptab = ctx->d_lptab.as<double>();
+    if (tables_cached) {
+        ++ctx->stats.table_cache_hits;
+        ctx->stats.lptab_entries = ctx->tab_entries;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+        ctx->P = P;
+        ctx->has_problem = true;
+        return DTO_B200_OK;
+    }
     // screen tables, then the log-p table: counts -> exclusive scan (host; a few hundred thousand words) -> fill
     const size_t cells = T1 * T2;
     CUDA_TRY(ctx->d_counts.ensure(cells * 4));
@@ -497,6 +523,13 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     ctx->stats.d2h_bytes += cells * 4;
     ctx->stats.lptab_entries = total;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    ctx->tab_N = population;
+    ctx->tab_levels = P.levels;
+    ctx->tab_never = P.never;
+    ctx->tab_entries = total;
+    ctx->tab_c1.swap(c1);
+    ctx->tab_c2.swap(c2);
+    ctx->tab_valid = true;
     ctx->P = P;
     ctx->has_problem = true;
     return DTO_B200_OK;

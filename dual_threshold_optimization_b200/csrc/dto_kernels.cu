@@ -496,7 +496,7 @@ struct __align__(16) Cand {
 
 template <int CH>
 struct ScanLayout {
-    static constexpr int CHP = CH + 2;           // even (64-bit column pairs) and CHP/2 odd for CH % 4 == 0
+    static constexpr int CHP = hist_words(CH);   // packed histogram words per lane (dto_device.cuh)
     static constexpr int QCAP = 32 * CH + 32;    // < 32 left-overs + one full row
     static constexpr int CAP = kCandCap;
     static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
@@ -840,7 +840,7 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         uint32_t kcur2[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) kcur2[q] = 0;
-        uint32_t koff = 0;
+        uint32_t koff2 = 0;  // overlap contributed by the lanes to the left, in both halves
         int level = 0;
 
         // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
@@ -860,7 +860,19 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         __syncwarp();
         issue_chunk(2);
         uint32_t cbase = 0, lo = 0;
-        uint2 *D2 = reinterpret_cast<uint2 *>(D + lane * CHP);  // this lane's column pairs (8-byte aligned: CHP even)
+        auto advance_ring = [&]() {  // chunk cbase is consumed: cbase+2 must have landed, refill the freed slot
+            ++cbase;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            issue_chunk(cbase + 2);
+        };
+        // this lane's words of the current row of critical overlaps (level `level`, row i), advanced row by row
+        auto kcrit_row = [&](int lvl, int r) {
+            return reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)lvl * P.T1 + r) * P.T2pad) + lane;
+        };
+        const uint32_t *__restrict__ kr = kcrit_row(0, 0);
+        const uint32_t kr_step = (uint32_t)P.T2pad >> 1;  // 32-bit words per row
+        uint4 *D4 = reinterpret_cast<uint4 *>(D + lane * CHP);  // this lane's column pairs, 4 per 128-bit vector
         // The row loop is call-free: when the queue holds a full chunk it BREAKS to the (out-of-line) drain and
         // re-enters, so the column state is only saved/restored around that rare call, never inside the loop.
         int i = 0;
@@ -869,47 +881,59 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
             const uint32_t hi = s_c1[i];
             // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
             // the scatter)
-            const uint32_t *__restrict__ kr =
-                reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
             uint32_t kc2[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) kc2[q] = __ldg(kr + q * 32);
-            // (1) bin this row's genes: position -> partner's column slot, privatised per warp
-            while (lo < hi) {
-                if ((lo / kChunk) > cbase) {  // chunk cbase is consumed: cbase+2 must have landed, refill its slot
-                    ++cbase;
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncwarp();
-                    issue_chunk(cbase + 2);
-                    continue;
-                }
-                const uint32_t e = hi < lo + 32 ? hi : lo + 32;
-                const uint32_t pos = lo + lane;
-                if (pos < e) {
+            kr += kr_step;
+            // (1) bin this row's genes: position -> partner's column slot, privatised per warp.  Positions below
+            // (cbase + 2) * kChunk are resident in the ring.
+            if ((lo / kChunk) > cbase) advance_ring();  // chunk cbase is consumed (once per row is enough to stay ahead)
+            for (;;) {
+                const uint32_t res = (cbase + 2) * kChunk, lim = hi < res ? hi : res;
+#pragma unroll 1
+                for (uint32_t pos = lo + lane; pos < lim; pos += 32) {
                     const uint32_t slot = ring[pos & (kRing - 1)];
-                    if (slot != kNoSlot) atomicAdd(&D[slot], 1u);
+                    if (slot != kNoSlot)
+                        atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(D) + (slot & 0xFFFCu)),
+                                  (slot & 1u) * 0xFFFFu + 1u);
                 }
-                lo = e;
+                lo = lim;
+                if (lo >= hi) break;
+                advance_ring();
             }
             __syncwarp();
-            // (2) 2-D inclusive prefix: lane-local run over its CH columns + warp exclusive scan of lane totals
-            uint32_t run = 0;
+            // (2) 2-D inclusive prefix, everything packed (two 16-bit counts per word; no field ever exceeds 65534):
+            // d = (x, y) of a column pair -> d * 0x10001 = (x, x + y); the running total rides in both halves.  Two
+            // independent half-length chains, the second one offset by the first one's total afterwards.
+            constexpr int NV = (NP + 3) / 4, HA = NP / 2;
+            uint32_t d[NV * 4];
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                const uint2 d = D2[q];
-                D2[q] = make_uint2(0u, 0u);
-                const uint32_t r0 = run + d.x;
-                run = r0 + d.y;
-                kcur2[q] += r0 + (run << 16);
+            for (int v = 0; v < NV; ++v) {
+                const uint4 t = D4[v];
+                D4[v] = make_uint4(0u, 0u, 0u, 0u);
+                d[4 * v] = t.x, d[4 * v + 1] = t.y, d[4 * v + 2] = t.z, d[4 * v + 3] = t.w;
             }
-            uint32_t inc = run;
+            uint32_t runA = 0, runB = 0;
+#pragma unroll
+            for (int q = 0; q < HA; ++q) {
+                const uint32_t t = d[q] * 0x10001u + runA;
+                kcur2[q] += t;
+                runA = __byte_perm(t, 0u, 0x3232);
+            }
+#pragma unroll
+            for (int q = HA; q < NP; ++q) {
+                const uint32_t t = d[q] * 0x10001u + runB;
+                kcur2[q] += t + runA;
+                runB = __byte_perm(t, 0u, 0x3232);
+            }
+            const uint32_t run2 = runA + runB;  // lane total in both halves
+            uint32_t inc2 = run2;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(kFull, inc, o);
-                if (lane >= o) inc += v;
+                const uint32_t v = __shfl_up_sync(kFull, inc2, o);
+                if (lane >= o) inc2 += v;
             }
-            koff += inc - run;
-            const uint32_t koff2 = koff * 0x10001u;
+            koff2 += inc2 - run2;
             // (3) screen: only k >= kcrit can have p <= tau_level
             auto screen = [&](int q) {
                 const uint32_t kk = kcur2[q] + koff2;  // no carry between the halves: every k < 65536
@@ -932,9 +956,24 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 uint32_t hit = 0;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) hit |= (kcur2[q] + bias - kc2[q]);
-                if (hit & 0x80008000u) {
+                if (hit & 0x80008000u) {  // some lane has a passing cell: revisit the pairs, each guarded by its own test
 #pragma unroll
-                    for (int q = 0; q < NP; ++q) screen(q);
+                    for (int q = 0; q < NP; ++q) {
+                        const uint32_t h = (kcur2[q] + bias - kc2[q]) & 0x80008000u;
+                        if (h) {
+                            const uint32_t kk = kcur2[q] + koff2;
+                            if (h & 0x8000u) {
+                                const uint32_t slot = atomicAdd(qcnt, 1u);
+                                Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q);
+                                Qk[slot] = (uint16_t)(kk & 0xFFFFu);
+                            }
+                            if (h >> 31) {
+                                const uint32_t slot = atomicAdd(qcnt, 1u);
+                                Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q + 1);
+                                Qk[slot] = (uint16_t)(kk >> 16);
+                            }
+                        }
+                    }
                 }
             } else {
 #pragma unroll
@@ -946,7 +985,10 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 break;
             }
         }
-        if (i < P.T1 || *qcnt >= 32) level = drain_queue(P, R, false, level);
+        if (i < P.T1 || *qcnt >= 32) {
+            level = drain_queue(P, R, false, level);
+            kr = kcrit_row(level, i);
+        }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         finish_task(P, R, task, level, record_flags, out, status, counters, task_stats, t_begin);
@@ -962,7 +1004,7 @@ __global__ void full_hist_kernel(const Problem P, const uint16_t *__restrict__ p
     const uint32_t slot = pbrow[j];
     const uint32_t b1 = P.bin1[j];
     if (slot == kNoSlot || b1 == kNoSlot) return;
-    const uint32_t col = (slot / P.CHP) * P.CH + (slot % P.CHP);
+    const uint32_t col = hist_slot_column(slot, P.CH);
     atomicAdd(&H[(size_t)b1 * P.T2 + col], 1u);
 }
 
@@ -1088,7 +1130,7 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
 }
 
 size_t scan_smem_bytes(int CH, int T1, int warps) {
-    const size_t chp = (size_t)(CH + 2);
+    const size_t chp = (size_t)hist_words(CH);
     const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
     const size_t q = ((size_t)(32 * CH + 32) * 6 + 15) & ~(size_t)15;
     const size_t per = d + q + 16 + (size_t)kCandCap * sizeof(Cand) + (size_t)kRing * 2;

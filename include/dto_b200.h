@@ -128,6 +128,8 @@ typedef struct dto_b200_stats {
     uint64_t h2d_bytes;         /* bytes copied host->device since create/reset (inputs, tables, task lists) */
     uint64_t d2h_bytes;         /* bytes copied device->host since create/reset (records, status words) */
     uint64_t lptab_entries;     /* size of the per-problem log-p lookup table (8 B each) */
+    uint64_t table_cache_hits;  /* set_problem calls that reused the previous problem's screen / log-p tables (same
+                                 * population and set sizes per threshold; option "table_cache" = 0 disables) */
 } dto_b200_stats;
 int dto_b200_get_stats(dto_b200_ctx *ctx, dto_b200_stats *out);
 int dto_b200_reset_stats(dto_b200_ctx *ctx);

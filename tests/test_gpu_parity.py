@@ -433,6 +433,32 @@ def test_batched_pairs_driver(engine):
         assert dto.run_pairs(pairs * 3, 150, devices=[0, 0, 0, 0], seed=rep) == dto.run_pairs(pairs * 3, 150, devices=[0], seed=rep)
 
 
+def test_table_cache_reuses_tables_only_when_set_sizes_match(engine):
+    """The screen / log-p tables depend on (population, set sizes per threshold) only: a second list pair with the same
+    tie-free rank structure reuses them (stats.table_cache_hits), a pair with ties rebuilds them, and records are
+    identical with the cache switched off."""
+    def records(cache):
+        eng = dto.Engine(0)
+        eng.set_option("table_cache", cache)
+        out = []
+        for seed, tied in ((1, 0.0), (2, 0.0), (3, 0.2), (4, 0.0)):
+            ids1, r1, ids2, r2 = H.synthetic_pair(1200, seed, 0.3 if seed % 2 else None, tied_frac=tied)
+            l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+            eng.load_lists(l1, l2, 1200)
+            recs = eng.run_permuted_philox(5, 0, 300)
+            out.append((eng.run_unpermuted().tobytes(), recs.tobytes()))
+            if seed == 2:
+                o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+                H.assert_record_matches(eng.run_unpermuted(), O.grid_int(o1, o2, 1200).best)
+        return out, eng.stats()["table_cache_hits"]
+
+    on, hits_on = records(1)
+    off, hits_off = records(0)
+    assert on == off
+    assert hits_off == 0
+    assert hits_on == 1  # pair 2 reuses pair 1's tables; the tied pair 3 and pair 4 (after 3) rebuild
+
+
 def test_generic_and_packed_screen_agree(engine, built):
     """The scan kernel has two screen code paths: packed 15-bit (set sizes <= 32766) and generic 16-bit (longer lists).
     Both must give identical records; the generic one is also what lists longer than 32 766 features use."""
