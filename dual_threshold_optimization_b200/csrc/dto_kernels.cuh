@@ -5,9 +5,13 @@
 
 namespace dto {
 
-constexpr int kScanThreads = 256;   // max threads per CTA of the scan kernel (8 warps = 8 permutations)
-constexpr int kScanCtasPerSm = 2;   // occupancy the scan kernel is compiled for: 128 registers/thread keep the column
-                                    // state out of local memory; 3 CTAs (85 registers) measured 1.2x slower
+#ifndef DTO_SCAN_THREADS
+#define DTO_SCAN_THREADS 320
+#endif
+constexpr int kScanThreads = DTO_SCAN_THREADS;  // max threads per CTA of the scan kernel (10 warps = 10 permutations)
+constexpr int kScanCtasPerSm = 2;   // occupancy the scan kernel is compiled for: 2 x 10 warps -> 96 registers/thread, which
+                                    // still keeps the column state of the row loop out of local memory (the few spills
+                                    // sit in the per-task prologue); 24 warps (80 registers) spill it and measured slower
 constexpr int kSigmaThreads = 1024; // one CTA per permutation in the pairing kernel
 constexpr int kCandCap = 64;        // per-warp shared-memory candidate buffer (entries)
 constexpr int kTaskStatWords = 8;   // per-task diagnostics words (option task_stats)
