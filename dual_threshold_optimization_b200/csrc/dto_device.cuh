@@ -56,11 +56,10 @@ struct Problem {
     const uint16_t *kcrit;     // [(levels+1)][T1][T2pad], column j stored at kcrit_col(j, CH)
     const uint2 *cellmeta;     // [T1*T2] {offset into lptab, kbase | count << 16}: log p tabulated for k in [kbase, kbase+count)
     const double *lptab;       // log p (ratio-recurrence tail, ~1e-10) for every (cell, k) between tau_1 and tau_levels
-    const uint16_t *dslot2;    // [n2] row-histogram slot of list-2 position (or kNoSlot)
+    const uint16_t *dslot2;    // [n2, padded to a multiple of 8] row-histogram slot of list-2 position (or kNoSlot)
     const uint16_t *bin1;      // [n1] threshold bin of list-1 position (or kNoSlot)
     const uint16_t *bin2;      // [n2]
     const int32_t *slot2_of_1; // [n1]
-    const uint32_t *rowstart_bits;  // [n1/32 + 2] bit p set iff list-1 position p starts a new threshold row (bin1[p] != bin1[p-1])
     double level_log[kMaxLevels + 1];  // log tau_l ; [0] = +inf
 };
 

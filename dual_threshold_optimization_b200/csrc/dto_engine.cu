@@ -95,7 +95,7 @@ struct dto_b200_ctx {
     bool has_problem = false;
     Problem P{};
     // problem tables
-    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts, d_rowbits;
+    DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts;
     // batch state
     DevBuf d_pb, d_records, d_status, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
         d_err, d_pair, d_minp, d_tstats, d_words;
@@ -272,7 +272,7 @@ void dto_b200_destroy(dto_b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_c1, &ctx->d_c2, &ctx->d_thr1, &ctx->d_thr2, &ctx->d_lf, &ctx->d_rowA, &ctx->d_colB,
-                      &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_rowbits, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
+                      &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
                       &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_H,
                       &ctx->d_pv, &ctx->d_logp, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_err, &ctx->d_pair,
                       &ctx->d_minp, &ctx->d_tstats, &ctx->d_words};
@@ -420,12 +420,10 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.n1_eff = c1[T1 - 1];
     P.never = (ctx->opt_swar && c1[T1 - 1] <= 32766u && c2[T2 - 1] <= 32766u) ? 0x7FFFu : 0xFFFFu;
     P.pb_stride = ((P.n1_eff + 1 + 255) / 256) * 256;  // whole staging chunks (cp.async in the scan), 512 B aligned rows
-    std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(((n2 ? n2 : 1) + 3) & ~(size_t)3, kNoSlot);
-    std::vector<uint32_t> rowbits(n1 / 32 + 2, 0u);
+    std::vector<uint16_t> bin1(n1 ? n1 : 1), bin2(n2 ? n2 : 1), dslot2(((n2 ? n2 : 1) + 7) & ~(size_t)7, kNoSlot);
     for (size_t j = 0; j < n1; ++j) {
         const size_t b = std::lower_bound(thr1, thr1 + T1, ranks1[j]) - thr1;
         bin1[j] = b < T1 ? (uint16_t)b : kNoSlot;
-        if (j > 0 && bin1[j] != bin1[j - 1]) rowbits[j >> 5] |= 1u << (j & 31);
     }
     for (size_t j = 0; j < n2; ++j) {
         const size_t b = std::lower_bound(thr2, thr2 + T2, ranks2[j]) - thr2;
@@ -472,7 +470,6 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     CUDA_TRY(up(ctx->d_dslot2, dslot2.data(), dslot2.size() * 2));
     CUDA_TRY(up(ctx->d_bin1, bin1.data(), bin1.size() * 2));
     CUDA_TRY(up(ctx->d_bin2, bin2.data(), bin2.size() * 2));
-    CUDA_TRY(up(ctx->d_rowbits, rowbits.data(), rowbits.size() * 4));
     CUDA_TRY(up(ctx->d_slot2, slot2_of_1, n1 * 4));  // n1 >= 1 here (T1 >= 1)
     CUDA_TRY(ctx->d_kcrit.ensure((size_t)(P.levels + 1) * T1 * P.T2pad * 2));
     P.c1 = ctx->d_c1.as<uint32_t>();
@@ -487,7 +484,6 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.bin1 = ctx->d_bin1.as<uint16_t>();
     P.bin2 = ctx->d_bin2.as<uint16_t>();
     P.slot2_of_1 = ctx->d_slot2.as<int32_t>();
-    P.rowstart_bits = ctx->d_rowbits.as<uint32_t>();
     P.cellmeta = ctx->d_meta.as<uint2>();
     P.lptab = ctx->d_lptab.as<double>();
     if (tables_cached) {
@@ -609,14 +605,14 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
     if (Pn == 0) return DTO_B200_OK;
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    // The sort buffer + boundary list of the pairing kernel live in a per-CTA global scratch (2 x nmax words, L2-
-    // resident): the row-wise fast path touches it for ~4 % of the elements only, and long lists would not fit it in
+    // The sort buffer, secondary keys and boundary list of the pairing kernel live in a per-CTA global scratch (L2-
+    // resident): the row-wise fast path touches it for ~5 % of the elements only, and long lists would not fit it in
     // shared memory anyway.
-    if (sigma_smem_bytes(P, B1, B2, false, false) > ctx->smem_optin)
+    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel needs %zu B of shared memory (> %zu)",
-                    sigma_smem_bytes(P, B1, B2, false, false), ctx->smem_optin);
+                    sigma_smem_bytes(P, B1, B2, false), ctx->smem_optin);
     const int sigma_grid_max = ctx->sm_count * 4;
-    CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * 3 * std::max(P.n1, P.n2) * 4));
+    CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * sigma_scratch_words(P) * 4));
     uint32_t *words_scratch = ctx->d_words.as<uint32_t>();
     const size_t batch = (size_t)auto_batch(ctx);
     ctx->stats.last_scan_kernel_ms = 0;
@@ -688,9 +684,9 @@ int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, 
     if (!pos2_of_pos1_out) return fail(DTO_B200_ERR_INVALID, "null output");
     const Problem &P = ctx->P;
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    if (sigma_smem_bytes(P, B1, B2, false, false) > ctx->smem_optin)
+    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
         return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel does not fit shared memory");
-    CUDA_TRY(ctx->d_words.ensure((size_t)3 * std::max(P.n1, P.n2) * 4));
+    CUDA_TRY(ctx->d_words.ensure(sigma_scratch_words(P) * 4));
     uint32_t *words_scratch = ctx->d_words.as<uint32_t>();
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
     CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));

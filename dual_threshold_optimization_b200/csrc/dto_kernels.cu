@@ -127,24 +127,30 @@ __global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ 
 
 // =====================================================================================================
 // K0: exactly-uniform random pairing by sorting Philox keys in shared memory.
-//   key(e) = 32 random bits.  Pass 1: bucket = top B bits (B ~ log2 n - 1, ~1.2 elements per bucket); ONE shared-
-//   memory atomic per element both counts the bucket and hands the element its arrival slot.  Pass 2: exclusive
-//   scan of the counts.  Pass 3: element -> words[off[bucket] + arrival] = (next 16 key bits << 16 | element).
-//   Pass 4: every element ranks itself inside its bucket on (16 key bits, secondary Philox key on a tie, index) --
-//   a total order, so the result does not depend on the order the atomics resolved in.
+//   Sort key of element e = (key16(e), sec32(e), e): key16 = one 16-bit half of a Philox4x32-10 word (stream s, one call
+//   per 8 elements), sec32 = a word of a second Philox stream (s + 8, one call per 4 elements), evaluated only where
+//   key16 does not decide.  i.i.d. keys + index tie-break = a uniform permutation (up to ~n^2 / 2^48).
+//   Pass 1: bucket = top B bits of key16 (B ~ log2 n - 1, ~1.2 elements per bucket); ONE shared-memory atomic per
+//   element both counts the bucket and hands the element its arrival slot; (key16, arrival) is kept per element so no
+//   later pass regenerates the primary keys.  Pass 2: exclusive scan of the counts.  Then either every element ranks
+//   itself inside its bucket (exact variant), or only the elements of buckets that straddle a threshold-row boundary do
+//   (row-wise variant, the hot path).
 // =====================================================================================================
 struct SortShared {
-    uint32_t *words;     // [n]     (rem16 << 16) | element, bucket-contiguous
-    uint32_t *cnt;       // [NB+1]  bucket counts, then offsets (exclusive scan)
-    uint16_t *arrival;   // [n]     arrival slot inside the bucket
+    uint32_t *cnt;       // [NB+1]  bucket counts, then offsets (exclusive scan); row-wise variant: bit 31 = "bucket
+                         //         straddles a row boundary"
+    uint32_t *ba;        // [8 * ceil(n/8)] (key16 << 16) | arrival slot inside the bucket, at ba_index(e)
     uint32_t *scan_tmp;  // [33]: [0..31] warp partials of the block scan, [32] = boundary-list counter
-    uint32_t *list;      // [n]     (global scratch) elements of buckets that straddle a row boundary: bucket << 16 | element
-    const uint32_t *rowbits;  // [n/32 + 2] shared copy of Problem::rowstart_bits
+    uint32_t *words;     // [n] (global scratch) ((key16 below the bucket bits) << 16) | element, bucket-contiguous
+    uint32_t *sec;       // [n] (global scratch) sec32 of the element at the same position
+    uint32_t *list;      // [n] (global scratch) elements of buckets that straddle a row boundary
 };
 
+constexpr uint32_t kPosMask = 0x7FFFFFFFu;
+
 __device__ __forceinline__ void philox_keys(uint32_t (&out)[4], uint64_t seed, uint64_t perm_id, uint32_t stream,
-                                            uint32_t block4) {
-    out[0] = block4;
+                                            uint32_t block) {
+    out[0] = block;
     out[1] = stream;
     out[2] = (uint32_t)perm_id;
     out[3] = (uint32_t)(perm_id >> 32);
@@ -155,6 +161,12 @@ __device__ __forceinline__ uint32_t secondary_key(uint64_t seed, uint64_t perm_i
     uint32_t c[4];
     philox_keys(c, seed, perm_id, stream + 8u, e >> 2);
     return c[e & 3u];
+}
+
+// (key16 | arrival) words are stored so that the two 128-bit accesses of the thread owning key block c8 = e / 8 are
+// contiguous across threads (conflict-free): half h = (e >> 2) & 1 of block c8 lives at uint4 index h * n8 + c8.
+__device__ __forceinline__ uint32_t ba_index(uint32_t e, uint32_t n8) {
+    return ((((e >> 2) & 1u) * n8 + (e >> 3)) << 2) | (e & 3u);
 }
 
 // exclusive scan of a[0..len) in place, a[len] = total; blockDim.x threads.  When len is a multiple of 4 * blockDim.x
@@ -221,154 +233,163 @@ __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     __syncthreads();
 }
 
-// 16-bit tie inside a bucket: fresh random bits (a second Philox stream) decide, then the index.  Kept out of line
-// so the common path carries no Philox evaluation.
-__device__ __noinline__ uint32_t rank_with_ties(const uint32_t *words, uint32_t lo, uint32_t hi, uint32_t e, uint32_t rem,
-                                                uint64_t seed, uint64_t perm_id, uint32_t stream) {
-    const uint32_t sec = secondary_key(seed, perm_id, stream, e);
-    uint32_t rank = 0;
-    for (uint32_t y = lo; y < hi; ++y) {
-        const uint32_t v = words[y];
-        const uint32_t ve = v & 0xFFFFu;
-        if ((v >> 16) < rem) {
-            ++rank;
-        } else if ((v >> 16) == rem && ve != e) {
-            const uint32_t os = secondary_key(seed, perm_id, stream, ve);
-            if (os < sec || (os == sec && ve < e)) ++rank;
-        }
-    }
-    return rank;
-}
-
-// Ranks the n elements of one Philox stream; calls emit(e, f): element e has the f-th smallest key.
-template <typename Emit>
-__device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id,
-                                          uint32_t stream, Emit emit) {
-    const uint32_t NB = 1u << B;
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    for (uint32_t x = tid; x <= NB; x += nt) S.cnt[x] = 0;
-    __syncthreads();
-    const uint32_t nblk = (n + 3) >> 2;
-    for (uint32_t c = tid; c < nblk; c += nt) {
-        uint32_t key[4];
-        philox_keys(key, seed, perm_id, stream, c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t e = c * 4 + q;
-            if (e < n) S.arrival[e] = (uint16_t)atomicAdd(&S.cnt[key[q] >> (32 - B)], 1u);
-        }
-    }
-    __syncthreads();
-    block_exclusive_scan(S.cnt, NB, S.scan_tmp);
-    for (uint32_t c = tid; c < nblk; c += nt) {
-        uint32_t key[4];
-        philox_keys(key, seed, perm_id, stream, c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t e = c * 4 + q;
-            if (e < n) {
-                const uint32_t pos = S.cnt[key[q] >> (32 - B)] + S.arrival[e];
-                S.words[pos] = (((key[q] >> (16 - B)) & 0xFFFFu) << 16) | e;
-            }
-        }
-    }
-    __syncthreads();
-    // pass 4, per element again (buckets hold ~1.2 members, so the scan of one's own bucket is 1-3 loads)
-    for (uint32_t c = tid; c < nblk; c += nt) {
-        uint32_t key[4];
-        philox_keys(key, seed, perm_id, stream, c);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t e = c * 4 + q;
-            if (e < n) {
-                const uint32_t b = key[q] >> (32 - B);
-                const uint32_t rem = (key[q] >> (16 - B)) & 0xFFFFu;
-                const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
-                uint32_t rank = 0;
-                bool tie = false;
-                for (uint32_t y = lo; y < hi; ++y) {
-                    const uint32_t v = S.words[y];
-                    rank += ((v >> 16) < rem) ? 1u : 0u;
-                    tie = tie || ((v >> 16) == rem && (v & 0xFFFFu) != e);
-                }
-                if (tie) rank = rank_with_ties(S.words, lo, hi, e, rem, seed, perm_id, stream);  // ~2^-16 per pair
-                emit(e, lo + rank);
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Fast path when only the ROW of every list-1 position matters (identical gene sets, no export): positions inside one
-// threshold row are interchangeable for the overlap grid, so an element whose whole bucket lies inside one row takes
-// position off[bucket] + arrival without being ranked (no third key pass, no sort-buffer traffic).  Only the ~4 % of
-// elements in buckets that straddle a row boundary are ranked exactly (words/list in the global scratch).  The result
-// is a uniform permutation up to within-row order; the records it leads to are identical to the exact path's.
-__device__ void block_place_rowwise(const SortShared &S, const Problem &P, uint32_t n, int B, uint64_t seed,
-                                    uint64_t perm_id, uint32_t stream, uint16_t *stage) {
+// Pass 1 + scan, shared by both variants: on return cnt[b] = first position of bucket b (cnt[NB] = n) and ba holds
+// (key16 << 16 | arrival) of every element.
+__device__ void block_bucket_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id, uint32_t stream) {
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     for (uint32_t x = tid; x <= NB; x += nt) S.cnt[x] = 0;
     if (tid == 0) S.scan_tmp[32] = 0;
     __syncthreads();
-    const uint32_t nblk = (n + 3) >> 2;
-    for (uint32_t c = tid; c < nblk; c += nt) {
+    const uint32_t n8 = (n + 7) >> 3;
+    uint4 *ba4 = reinterpret_cast<uint4 *>(S.ba);
+    for (uint32_t c = tid; c < n8; c += nt) {
         uint32_t key[4];
         philox_keys(key, seed, perm_id, stream, c);
+        uint32_t v[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t e = c * 4 + q;
-            if (e < n) S.arrival[e] = (uint16_t)atomicAdd(&S.cnt[key[q] >> (32 - B)], 1u);
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t e = c * 8 + q;
+            const uint32_t k16 = (q & 1) ? (key[q >> 1] >> 16) : (key[q >> 1] & 0xFFFFu);
+            v[q] = k16 << 16;
+            if (e < n) v[q] |= atomicAdd(&S.cnt[k16 >> (16 - B)], 1u);
         }
+        ba4[c] = make_uint4(v[0], v[1], v[2], v[3]);
+        ba4[n8 + c] = make_uint4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
     block_exclusive_scan(S.cnt, NB, S.scan_tmp);
+}
+
+// rank of (rem, sec, e) among the members of its bucket [lo, hi): a total order, so the result does not depend on the
+// order the atomics resolved in
+__device__ __forceinline__ uint32_t rank_in_bucket(const SortShared &S, uint32_t lo, uint32_t hi, uint32_t word,
+                                                   uint32_t sec) {
+    uint32_t rank = 0;
+    for (uint32_t y = lo; y < hi; ++y) {
+        const uint32_t w = S.words[y];
+        if (w == word) continue;  // itself (the element index makes every word unique)
+        const uint32_t a = w >> 16, b = word >> 16;
+        if (a != b) {
+            rank += (a < b) ? 1u : 0u;
+        } else {
+            const uint32_t os = S.sec[y];
+            rank += (os < sec || (os == sec && (w & 0xFFFFu) < (word & 0xFFFFu))) ? 1u : 0u;
+        }
+    }
+    return rank;
+}
+
+// Exact variant: ranks the n elements of one Philox stream; calls emit(e, f): element e has the f-th smallest key.
+template <typename Emit>
+__device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id,
+                                          uint32_t stream, Emit emit) {
+    block_bucket_keys(S, n, B, seed, perm_id, stream);
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t n8 = (n + 7) >> 3, nblk = (n + 3) >> 2, remmask = (1u << (16 - B)) - 1u;
     for (uint32_t c = tid; c < nblk; c += nt) {
-        uint32_t key[4];
-        philox_keys(key, seed, perm_id, stream, c);
-        // partner slots of the 4 elements of this key block: one 8-byte load (dslot2 is padded to a multiple of 4)
-        const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + (size_t)c * 4);
-        const uint16_t ds[4] = {(uint16_t)(dsv.x & 0xFFFFu), (uint16_t)(dsv.x >> 16), (uint16_t)(dsv.y & 0xFFFFu), (uint16_t)(dsv.y >> 16)};
+        uint32_t sk[4];
+        philox_keys(sk, seed, perm_id, stream + 8u, c);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint32_t e = c * 4 + q;
             if (e < n) {
-                const uint32_t b = key[q] >> (32 - B);
-                const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
-                const uint32_t pos = lo + S.arrival[e];
-                // single-row bucket <=> no row starts at positions lo+1 .. hi-1 (bitmap window of <= 32 bits)
-                const uint32_t span = hi - lo - 1;
-                bool single = span == 0;
-                if (!single && span <= 32) {
-                    const uint32_t w = (lo + 1) >> 5, sh = (lo + 1) & 31;
-                    const uint32_t win = __funnelshift_r(S.rowbits[w], S.rowbits[w + 1], sh);
-                    single = (win & (span == 32 ? 0xFFFFFFFFu : ((1u << span) - 1u))) == 0;
+                const uint32_t v = S.ba[ba_index(e, n8)];
+                const uint32_t pos = S.cnt[v >> (32 - B)] + (v & 0xFFFFu);
+                S.words[pos] = (((v >> 16) & remmask) << 16) | e;
+                S.sec[pos] = sk[q];
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < n; e += nt) {
+        const uint32_t v = S.ba[ba_index(e, n8)];
+        const uint32_t b = v >> (32 - B);
+        const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
+        uint32_t rank = 0;
+        if (hi - lo > 1) {
+            const uint32_t pos = lo + (v & 0xFFFFu);
+            rank = rank_in_bucket(S, lo, hi, S.words[pos], S.sec[pos]);
+        }
+        emit(e, lo + rank);
+    }
+    __syncthreads();
+}
+
+// Row-wise variant, used when only the ROW of every list-1 position matters (identical gene sets, no export): positions
+// inside one threshold row are interchangeable for the overlap grid, so an element whose whole bucket lies inside one
+// row takes position off[bucket] + arrival without being ranked.  Buckets that contain a row boundary strictly inside
+// are found from the boundaries' side (one binary search over the bucket offsets per threshold, `bounds` = Problem::c1);
+// only their elements (~5 %) get a secondary key and an exact rank.  The result is the exact variant's permutation up
+// to within-row order; the records it leads to are identical.
+__device__ void block_place_rowwise(const SortShared &S, const Problem &P, const uint32_t *bounds, uint32_t n, int B,
+                                    uint64_t seed, uint64_t perm_id, uint32_t stream, uint16_t *stage) {
+    block_bucket_keys(S, n, B, seed, perm_id, stream);
+    const uint32_t NB = 1u << B;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    // flag the buckets a row boundary p cuts (off[b] < p < off[b+1]); T1 <= 2048 = 2 boundaries per thread
+    uint32_t cut[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t x = tid + (uint32_t)r * nt;
+        if (x < (uint32_t)P.T1) {
+            const uint32_t p = bounds[x];
+            if (p > 0 && p < n) {
+                uint32_t lo = 0, hi = NB;  // largest b with off[b] <= p: the (non-empty) bucket holding position p
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (S.cnt[mid] <= p) lo = mid;
+                    else hi = mid;
                 }
-                if (single) {
-                    if (pos < P.n1_eff) stage[pos] = ds[q];
+                if (S.cnt[lo] < p) cut[r] = lo;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+        if (cut[r] != 0xFFFFFFFFu) atomicOr(&S.cnt[cut[r]], 0x80000000u);
+    __syncthreads();
+    const uint32_t n8 = (n + 7) >> 3;
+    const uint4 *ba4 = reinterpret_cast<const uint4 *>(S.ba);
+    for (uint32_t c = tid; c < n8; c += nt) {
+        const uint4 va = ba4[c], vb = ba4[n8 + c];
+        const uint32_t v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        // partner slots of the 8 elements of this key block: one 16-byte load (dslot2 is padded to a multiple of 8)
+        const uint4 dsv = *reinterpret_cast<const uint4 *>(P.dslot2 + (size_t)c * 8);
+        const uint32_t dsw[4] = {dsv.x, dsv.y, dsv.z, dsv.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t e = c * 8 + q;
+            if (e < n) {
+                const uint32_t w = S.cnt[v[q] >> (32 - B)];
+                if (!(w >> 31)) {
+                    const uint32_t pos = w + (v[q] & 0xFFFFu);
+                    if (pos < P.n1_eff) stage[pos] = (uint16_t)((q & 1) ? (dsw[q >> 1] >> 16) : (dsw[q >> 1] & 0xFFFFu));
                 } else {
-                    S.words[pos] = (((key[q] >> (16 - B)) & 0xFFFFu) << 16) | e;
-                    S.list[atomicAdd(&S.scan_tmp[32], 1u)] = (b << 16) | e;
+                    S.list[atomicAdd(&S.scan_tmp[32], 1u)] = e;
                 }
             }
         }
     }
     __syncthreads();
-    const uint32_t n_list = S.scan_tmp[32];
+    const uint32_t n_list = S.scan_tmp[32], remmask = (1u << (16 - B)) - 1u;
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t ent = S.list[x];
-        const uint32_t e = ent & 0xFFFFu, b = ent >> 16;
-        const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
-        const uint32_t rem = S.words[lo + S.arrival[e]] >> 16;
-        uint32_t rank = 0;
-        bool tie = false;
-        for (uint32_t y = lo; y < hi; ++y) {
-            const uint32_t v = S.words[y];
-            rank += ((v >> 16) < rem) ? 1u : 0u;
-            tie = tie || ((v >> 16) == rem && (v & 0xFFFFu) != e);
-        }
-        if (tie) rank = rank_with_ties(S.words, lo, hi, e, rem, seed, perm_id, stream);
-        if (lo + rank < P.n1_eff) stage[lo + rank] = P.dslot2[e];
+        const uint32_t e = S.list[x];
+        const uint32_t v = S.ba[ba_index(e, n8)];
+        const uint32_t pos = (S.cnt[v >> (32 - B)] & kPosMask) + (v & 0xFFFFu);
+        S.words[pos] = (((v >> 16) & remmask) << 16) | e;
+        S.sec[pos] = secondary_key(seed, perm_id, stream, e);
+    }
+    __syncthreads();
+    for (uint32_t x = tid; x < n_list; x += nt) {
+        const uint32_t e = S.list[x];
+        const uint32_t v = S.ba[ba_index(e, n8)];
+        const uint32_t b = v >> (32 - B);
+        const uint32_t lo = S.cnt[b] & kPosMask, hi = S.cnt[b + 1] & kPosMask;
+        const uint32_t pos = lo + (v & 0xFFFFu);
+        const uint32_t f = lo + rank_in_bucket(S, lo, hi, S.words[pos], S.sec[pos]);
+        if (f < P.n1_eff) stage[f] = P.dslot2[e];
     }
     __syncthreads();
 }
@@ -377,39 +398,40 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
                                                                    uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
                                                                    uint32_t *__restrict__ pairing_out,
-                                                                   uint32_t *__restrict__ words_scratch,
-                                                                   int arrival_in_scratch) {
+                                                                   uint32_t *__restrict__ scratch_base,
+                                                                   int ba_in_scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+    const uint32_t nmax8 = (nmax + 7) & ~7u;
     const int Bmax = B1 > B2 ? B1 : B2;
-    // layout: cnt[NB+1] | scan_tmp[33] | stage[stage_len] u16 | arrival[nmax] u16 | order2[n_common] u16 | words[nmax] u32
-    // (words and the boundary list live in the per-CTA global scratch when it is given)
+    // shared: cnt[NB+1] | scan_tmp[33] | pad | stage[pb_stride] u16 | bounds[T1] u32 | order2[n_common] u16 | ba[nmax8] u32
+    // per-CTA global scratch (L2-resident): words[nmax8] | sec[nmax8] | list[nmax8] | ba[nmax8] (when it does not fit)
     SortShared S;
     S.cnt = reinterpret_cast<uint32_t *>(smem_raw);
     S.scan_tmp = S.cnt + (1u << Bmax) + 1;
-    const uint32_t stage_len = P.pb_stride;
-    uint16_t *stage = reinterpret_cast<uint16_t *>(S.scan_tmp + 33);  // (NB + 1 + 33) words: 8-byte aligned for B >= 1
-    // per-CTA global scratch: words[nmax] | list[nmax] | arrival[nmax] (u16, only when it does not fit shared memory)
-    uint32_t *scratch = words_scratch ? words_scratch + (size_t)blockIdx.x * 3 * nmax : nullptr;
+    size_t off = (((size_t)(1u << Bmax) + 1 + 33) * 4 + 15) & ~(size_t)15;
+    uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + off);  // pb_stride is a multiple of 256: 16 B aligned end
+    off += (size_t)P.pb_stride * 2;
+    uint32_t *bounds = reinterpret_cast<uint32_t *>(smem_raw + off);
+    off += (((size_t)P.T1 * 4) + 15) & ~(size_t)15;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
-    uint16_t *arr_smem = stage + stage_len;  // pb_stride is a multiple of 256
-    S.arrival = arrival_in_scratch ? reinterpret_cast<uint16_t *>(scratch + 2 * (size_t)nmax) : arr_smem;
-    uint16_t *order2 = arr_smem + (arrival_in_scratch ? 0u : ((nmax + 3) & ~3u));
-    uint16_t *after = order2 + (identical ? 0u : ((P.n_common + 3) & ~3u));
-    S.words = scratch ? scratch : reinterpret_cast<uint32_t *>(after) + (P.n1 / 32 + 2);
-    S.list = scratch ? scratch + nmax : nullptr;
-    uint32_t *rowbits = reinterpret_cast<uint32_t *>(after);  // [n1/32 + 2]
-    S.rowbits = rowbits;
-    for (uint32_t x = threadIdx.x; x < P.n1 / 32 + 2; x += blockDim.x) rowbits[x] = P.rowstart_bits[x];
+    uint16_t *order2 = reinterpret_cast<uint16_t *>(smem_raw + off);
+    if (!identical) off += (((size_t)P.n_common * 2) + 15) & ~(size_t)15;
+    uint32_t *scratch = scratch_base + (size_t)blockIdx.x * 4 * nmax8;
+    S.words = scratch;
+    S.sec = scratch + nmax8;
+    S.list = scratch + 2 * (size_t)nmax8;
+    S.ba = ba_in_scratch ? scratch + 3 * (size_t)nmax8 : reinterpret_cast<uint32_t *>(smem_raw + off);
+    for (uint32_t x = threadIdx.x; x < (uint32_t)P.T1; x += blockDim.x) bounds[x] = P.c1[x];
     __syncthreads();
-    const bool rowwise = identical && pairing_out == nullptr && words_scratch != nullptr;
+    const bool rowwise = identical && pairing_out == nullptr;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
 
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const uint64_t perm_id = first_id + (uint64_t)t;
         uint16_t *dst = pb + (size_t)t * P.pb_stride;
         if (rowwise) {
-            block_place_rowwise(S, P, P.n2, B2, seed, perm_id, 0u, stage);
+            block_place_rowwise(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
             for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
         } else if (identical) {
             // element = list-2 position e, rank f = the list-1 position it is paired with
@@ -1181,18 +1203,24 @@ cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *
     return cudaGetLastError();
 }
 
-// shared-memory bytes of the pairing kernel; words_in_smem = false moves the n x 4 B sort buffer to a global scratch
-size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem, bool arrival_in_smem) {
+// shared-memory bytes of the pairing kernel; ba_in_smem = false moves the n x 4 B (key16 | arrival) array to the
+// per-CTA global scratch (long lists)
+size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool ba_in_smem) {
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const int Bmax = B1 > B2 ? B1 : B2;
-    size_t b = ((size_t)(1u << Bmax) + 1 + 33) * 4;
+    size_t b = (((size_t)(1u << Bmax) + 1 + 33) * 4 + 15) & ~(size_t)15;
     b += (size_t)P.pb_stride * 2;
-    if (arrival_in_smem) b += (size_t)((nmax + 3) & ~3u) * 2;
+    b += (((size_t)P.T1 * 4) + 15) & ~(size_t)15;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
-    if (!identical) b += (size_t)((P.n_common + 3) & ~3u) * 2;
-    b += (size_t)(P.n1 / 32 + 2) * 4;
-    if (words_in_smem) b += (size_t)nmax * 4;
+    if (!identical) b += (((size_t)P.n_common * 2) + 15) & ~(size_t)15;
+    if (ba_in_smem) b += (size_t)((nmax + 7) & ~7u) * 4;
     return (b + 15) & ~(size_t)15;
+}
+
+// u32 words of global scratch one CTA of the pairing kernel needs
+size_t sigma_scratch_words(const Problem &P) {
+    const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+    return (size_t)4 * ((nmax + 7) & ~7u);
 }
 
 int pick_bucket_bits(uint32_t n) {
@@ -1205,16 +1233,15 @@ int pick_bucket_bits(uint32_t n) {
 }
 
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
-                              uint32_t *pairing_out, uint32_t *words_scratch, size_t smem_limit, int grid,
-                              cudaStream_t st) {
+                              uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit, int grid, cudaStream_t st) {
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    const bool arrival_in_smem = sigma_smem_bytes(P, B1, B2, false, true) <= smem_limit;
-    const size_t smem = sigma_smem_bytes(P, B1, B2, false, arrival_in_smem);
-    if (smem > smem_limit || !words_scratch) return cudaErrorInvalidValue;
+    const bool ba_in_smem = sigma_smem_bytes(P, B1, B2, true) <= smem_limit;
+    const size_t smem = sigma_smem_bytes(P, B1, B2, ba_in_smem);
+    if (smem > smem_limit || !scratch) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
-    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, words_scratch,
-                                                        arrival_in_smem ? 0 : 1);
+    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, scratch,
+                                                        ba_in_smem ? 0 : 1);
     return cudaGetLastError();
 }
 

@@ -21,13 +21,13 @@ constexpr int kRing = 4 * kChunk;   // per-warp staging ring of partner slots (u
 int pick_ch(int T2);
 int pick_bucket_bits(uint32_t n);
 size_t scan_smem_bytes(int CH, int T1, int warps);
-size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool words_in_smem, bool arrival_in_smem);
+size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool ba_in_smem);
+size_t sigma_scratch_words(const Problem &P);
 
 cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *counts, uint2 *meta, cudaStream_t st);
 cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *meta, double *lptab, cudaStream_t st);
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
-                              uint32_t *pairing_out, uint32_t *words_scratch, size_t smem_limit, int grid,
-                              cudaStream_t st);
+                              uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit, int grid, cudaStream_t st);
 cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, int n_tasks,
                            uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st);
 cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags, dto_b200_record *out,

@@ -137,23 +137,29 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def device_keys(n, seed, perm_id, stream):
-    """The 32-bit sort key of every element, as the pairing kernel derives it: counter = (element / 4, stream, id lo, id hi),
-    key = (seed lo, seed hi), word element % 4."""
+    """One 32-bit Philox word per element: counter = (element / 4, stream, id lo, id hi), key = (seed lo, seed hi),
+    word element % 4 (the SECONDARY sort key of the pairing kernel uses stream + 8)."""
     blk = np.arange((n + 3) // 4, dtype=np.uint64)
     out = philox4x32_10(blk, np.full_like(blk, stream), np.full_like(blk, perm_id & 0xFFFFFFFF), np.full_like(blk, perm_id >> 32),
                         seed & 0xFFFFFFFF, seed >> 32)
     return np.stack(out, axis=1).reshape(-1)[:n]
 
 
+def device_keys16(n, seed, perm_id, stream):
+    """The 16-bit PRIMARY sort key of every element: one Philox call per 8 elements (counter = (element / 8, stream, id lo,
+    id hi)); element e takes word (e % 8) / 2, low half when e is even, high half when odd."""
+    blk = np.arange((n + 7) // 8, dtype=np.uint64)
+    out = philox4x32_10(blk, np.full_like(blk, stream), np.full_like(blk, perm_id & 0xFFFFFFFF), np.full_like(blk, perm_id >> 32),
+                        seed & 0xFFFFFFFF, seed >> 32)
+    words = np.stack(out, axis=1)  # [n8, 4]
+    halves = np.stack([words & np.uint64(0xFFFF), words >> np.uint64(16)], axis=2)  # [n8, 4, 2]
+    return halves.reshape(-1)[:n]
+
+
 def expected_pairing_identical(n, seed, perm_id):
     """pos2_of_pos1 for identical gene sets: list-1 position f is paired with the list-2 position whose key has rank f.
-    Order = (top B + 16 key bits, secondary Philox key (stream + 8), index), B = bucket bits of the kernel."""
-    lg = 0
-    while (1 << lg) < n:
-        lg += 1
-    B = min(14, max(1, lg - 1))
-    key = device_keys(n, seed, perm_id, 0)
+    Order = (16-bit primary key, 32-bit secondary Philox key (stream + 8), index)."""
+    key = device_keys16(n, seed, perm_id, 0)
     sec = device_keys(n, seed, perm_id, 8)
-    primary = key >> np.uint64(16 - B)
-    order = np.lexsort((np.arange(n), sec, primary))
+    order = np.lexsort((np.arange(n), sec, key))
     return order.astype(np.uint32)
