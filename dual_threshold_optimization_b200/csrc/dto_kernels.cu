@@ -521,7 +521,8 @@ struct ScanLayout {
     static constexpr int CHP = hist_words(CH);   // packed histogram words per lane (dto_device.cuh)
     static constexpr int QCAP = 32 * CH + 32;    // < 32 left-overs + one full row
     static constexpr int CAP = kCandCap;
-    static constexpr size_t d_bytes = ((size_t)32 * CHP * 4 + 15) & ~(size_t)15;
+    static constexpr uint32_t dummy_off = 32u * CHP * 4u;  // byte offset of the sink word that absorbs kNoSlot partners
+    static constexpr size_t d_bytes = (size_t)32 * CHP * 4 + 16;  // CHP is a multiple of 4: 16-byte multiple
     static constexpr size_t q_bytes = ((size_t)QCAP * 6 + 15) & ~(size_t)15;  // u32 (row<<16|col) + u16 k per entry
     static constexpr size_t ring_bytes = (size_t)kRing * 2;  // partner-slot staging ring (cp.async), 4 chunks of kChunk
     static constexpr size_t per_warp = d_bytes + q_bytes + 16 + (size_t)CAP * sizeof(Cand) + ring_bytes;
@@ -863,6 +864,7 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
 #pragma unroll
         for (int q = 0; q < NP; ++q) kcur2[q] = 0;
         uint32_t koff2 = 0;  // overlap contributed by the lanes to the left, in both halves
+        uint32_t qn = 0;     // warp-uniform copy of *qcnt (refreshed only after rows that pushed something)
         int level = 0;
 
         // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
@@ -914,10 +916,11 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 const uint32_t res = (cbase + 2) * kChunk, lim = hi < res ? hi : res;
 #pragma unroll 1
                 for (uint32_t pos = lo + lane; pos < lim; pos += 32) {
+                    // kNoSlot (partner beyond the last list-2 threshold) lands in a sink word past the histogram
                     const uint32_t slot = ring[pos & (kRing - 1)];
-                    if (slot != kNoSlot)
-                        atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(D) + (slot & 0xFFFCu)),
-                                  (slot & 1u) * 0xFFFFu + 1u);
+                    const uint32_t off = min(slot & 0xFFFCu, L::dummy_off);
+                    atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(D) + off),
+                              (slot & 1u) * 0xFFFFu + 1u);
                 }
                 lo = lim;
                 if (lo >= hi) break;
@@ -978,7 +981,8 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 uint32_t hit = 0;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) hit |= (kcur2[q] + bias - kc2[q]);
-                if (hit & 0x80008000u) {  // some lane has a passing cell: revisit the pairs, each guarded by its own test
+                if (__any_sync(kFull, (hit & 0x80008000u) != 0u)) {  // some lane has a passing cell (8 % of the rows)
+                  if (hit & 0x80008000u) {  // revisit the pairs, each guarded by its own test
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         const uint32_t h = (kcur2[q] + bias - kc2[q]) & 0x80008000u;
@@ -996,20 +1000,26 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                             }
                         }
                     }
+                  }
+                  __syncwarp();
+                  qn = *qcnt;
                 }
             } else {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) screen(q);
+                __syncwarp();
+                qn = *qcnt;
             }
-            __syncwarp();
-            if (*qcnt >= 32) {
+            if (qn >= 32) {
                 ++i;
                 break;
             }
         }
-        if (i < P.T1 || *qcnt >= 32) {
+        if (qn >= 32) {
             level = drain_queue(P, R, false, level);
             kr = kcrit_row(level, i);
+            __syncwarp();
+            qn = *qcnt;
         }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1153,7 +1163,7 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
 
 size_t scan_smem_bytes(int CH, int T1, int warps) {
     const size_t chp = (size_t)hist_words(CH);
-    const size_t d = (32 * chp * 4 + 15) & ~(size_t)15;
+    const size_t d = 32 * chp * 4 + 16;
     const size_t q = ((size_t)(32 * CH + 32) * 6 + 15) & ~(size_t)15;
     const size_t per = d + q + 16 + (size_t)kCandCap * sizeof(Cand) + (size_t)kRing * 2;
     return (((size_t)T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * per;
