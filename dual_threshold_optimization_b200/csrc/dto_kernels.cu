@@ -13,6 +13,8 @@
 //                              also the last-resort path for degenerate tasks (min p >= 1)
 #include "dto_kernels.cuh"
 
+#include <algorithm>
+
 namespace dto {
 
 // =====================================================================================================
@@ -139,11 +141,14 @@ __global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ 
 struct SortShared {
     uint32_t *cnt;       // [NB+1]  bucket counts, then offsets (exclusive scan); row-wise variant: bit 31 = "bucket
                          //         straddles a row boundary"
-    uint32_t *ba;        // [8 * ceil(n/8)] (key16 << 16) | arrival slot inside the bucket, at ba_index(e)
+    uint32_t *ba;        // [8 * ceil(n/8)] (key16 << 16) | arrival slot inside the bucket, at ba_index(e); the row-wise
+                         //         variant later replaces the entries of boundary-bucket elements by their tie-break word
     uint32_t *scan_tmp;  // [33]: [0..31] warp partials of the block scan, [32] = boundary-list counter
-    uint32_t *words;     // [n] (global scratch) ((key16 below the bucket bits) << 16) | element, bucket-contiguous
-    uint32_t *sec;       // [n] (global scratch) sec32 of the element at the same position
-    uint32_t *list;      // [n] (global scratch) elements of buckets that straddle a row boundary
+    uint32_t *list_s;    // [list_cap] (shared) boundary-bucket elements: bucket << 16 | element, later position << 16 | element
+    uint32_t *list_g;    // [n] (global scratch) the same list beyond list_cap entries
+    uint32_t list_cap;
+    uint32_t *words;     // [n] (global scratch, exact variant) element at each position, bucket-contiguous
+    uint32_t *tie;       // [n] (global scratch, exact variant) tie-break word of every element
 };
 
 constexpr uint32_t kPosMask = 0x7FFFFFFFu;
@@ -163,30 +168,35 @@ __device__ __forceinline__ uint32_t secondary_key(uint64_t seed, uint64_t perm_i
     return c[e & 3u];
 }
 
+// Order inside a bucket = (tie-break word, element index); the word = the key16 bits below the bucket bits, followed by
+// the top 16 + B bits of the secondary key.  Overall order = (key16, sec32 >> (16 - B), index).
+__device__ __forceinline__ uint32_t tie_word(uint32_t key16, uint32_t sec32, int B) {
+    return ((key16 & ((1u << (16 - B)) - 1u)) << (16 + B)) | (sec32 >> (16 - B));
+}
+
 // (key16 | arrival) words are stored so that the two 128-bit accesses of the thread owning key block c8 = e / 8 are
 // contiguous across threads (conflict-free): half h = (e >> 2) & 1 of block c8 lives at uint4 index h * n8 + c8.
 __device__ __forceinline__ uint32_t ba_index(uint32_t e, uint32_t n8) {
     return ((((e >> 2) & 1u) * n8 + (e >> 3)) << 2) | (e & 3u);
 }
 
-// exclusive scan of a[0..len) in place, a[len] = total; blockDim.x threads.  When len is a multiple of 4 * blockDim.x
-// every thread owns a contiguous run held in registers (128-bit shared loads/stores); otherwise a plain serial run.
-__device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
+// exclusive scan of a[0..len) in place, a[len] = total; blockDim.x threads.  V > 0: every thread owns a contiguous run
+// of 4 * V counters held in registers (128-bit shared loads/stores, len == 4 * V * blockDim.x); V == 0: plain serial runs.
+template <int V>
+__device__ void block_exclusive_scan_t(uint32_t *a, uint32_t len, uint32_t *tmp) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t lane = tid & 31, w = tid >> 5;
-    const bool vec = (len % (4 * nt)) == 0 && len / nt <= 16;
-    const uint32_t per = vec ? len / nt : (len + nt - 1) / nt;
-    const uint32_t b = tid * per, e = (b + per < len) ? b + per : len;
-    uint4 r[4];
+    const uint32_t per = V > 0 ? 4u * V : (len + nt - 1) / nt;
+    const uint32_t b = tid * per < len ? tid * per : len, e = (b + per < len) ? b + per : len;
+    uint4 r[V > 0 ? V : 1];
     uint32_t sum = 0;
-    if (vec) {
+    if (V > 0) {
         const uint4 *a4 = reinterpret_cast<const uint4 *>(a + b);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if ((uint32_t)q * 4 < per) {
-                r[q] = a4[q];
-                sum += r[q].x + r[q].y + r[q].z + r[q].w;
-            }
+        for (int q = 0; q < V; ++q) {
+            r[q] = a4[q];
+            sum += r[q].x + r[q].y + r[q].z + r[q].w;
+        }
     } else {
         for (uint32_t x = b; x < e; ++x) sum += a[x];
     }
@@ -209,19 +219,18 @@ __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     }
     __syncthreads();
     uint32_t run = tmp[w] + inc - sum;
-    if (vec) {
+    if (V > 0) {
         uint4 *a4 = reinterpret_cast<uint4 *>(a + b);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if ((uint32_t)q * 4 < per) {
-                uint4 o;
-                o.x = run;
-                o.y = o.x + r[q].x;
-                o.z = o.y + r[q].y;
-                o.w = o.z + r[q].z;
-                run = o.w + r[q].w;
-                a4[q] = o;
-            }
+        for (int q = 0; q < V; ++q) {
+            uint4 o;
+            o.x = run;
+            o.y = o.x + r[q].x;
+            o.z = o.y + r[q].y;
+            o.w = o.z + r[q].z;
+            run = o.w + r[q].w;
+            a4[q] = o;
+        }
     } else {
         for (uint32_t x = b; x < e; ++x) {
             const uint32_t v = a[x];
@@ -231,6 +240,14 @@ __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     }
     if (tid == nt - 1) a[len] = run;  // the last thread's run ends at len (or is empty): run == total
     __syncthreads();
+}
+
+__device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
+    const uint32_t nt = blockDim.x;
+    if (len == 16 * nt) block_exclusive_scan_t<4>(a, len, tmp);
+    else if (len == 8 * nt) block_exclusive_scan_t<2>(a, len, tmp);
+    else if (len == 4 * nt) block_exclusive_scan_t<1>(a, len, tmp);
+    else block_exclusive_scan_t<0>(a, len, tmp);
 }
 
 // Pass 1 + scan, shared by both variants: on return cnt[b] = first position of bucket b (cnt[NB] = n) and ba holds
@@ -261,32 +278,13 @@ __device__ void block_bucket_keys(const SortShared &S, uint32_t n, int B, uint64
     block_exclusive_scan(S.cnt, NB, S.scan_tmp);
 }
 
-// rank of (rem, sec, e) among the members of its bucket [lo, hi): a total order, so the result does not depend on the
-// order the atomics resolved in
-__device__ __forceinline__ uint32_t rank_in_bucket(const SortShared &S, uint32_t lo, uint32_t hi, uint32_t word,
-                                                   uint32_t sec) {
-    uint32_t rank = 0;
-    for (uint32_t y = lo; y < hi; ++y) {
-        const uint32_t w = S.words[y];
-        if (w == word) continue;  // itself (the element index makes every word unique)
-        const uint32_t a = w >> 16, b = word >> 16;
-        if (a != b) {
-            rank += (a < b) ? 1u : 0u;
-        } else {
-            const uint32_t os = S.sec[y];
-            rank += (os < sec || (os == sec && (w & 0xFFFFu) < (word & 0xFFFFu))) ? 1u : 0u;
-        }
-    }
-    return rank;
-}
-
 // Exact variant: ranks the n elements of one Philox stream; calls emit(e, f): element e has the f-th smallest key.
 template <typename Emit>
 __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id,
                                           uint32_t stream, Emit emit) {
     block_bucket_keys(S, n, B, seed, perm_id, stream);
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const uint32_t n8 = (n + 7) >> 3, nblk = (n + 3) >> 2, remmask = (1u << (16 - B)) - 1u;
+    const uint32_t n8 = (n + 7) >> 3, nblk = (n + 3) >> 2;
     for (uint32_t c = tid; c < nblk; c += nt) {
         uint32_t sk[4];
         philox_keys(sk, seed, perm_id, stream + 8u, c);
@@ -295,9 +293,8 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
             const uint32_t e = c * 4 + q;
             if (e < n) {
                 const uint32_t v = S.ba[ba_index(e, n8)];
-                const uint32_t pos = S.cnt[v >> (32 - B)] + (v & 0xFFFFu);
-                S.words[pos] = (((v >> 16) & remmask) << 16) | e;
-                S.sec[pos] = sk[q];
+                S.words[S.cnt[v >> (32 - B)] + (v & 0xFFFFu)] = e;
+                S.tie[e] = tie_word(v >> 16, sk[q], B);
             }
         }
     }
@@ -308,8 +305,12 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
         const uint32_t lo = S.cnt[b], hi = S.cnt[b + 1];
         uint32_t rank = 0;
         if (hi - lo > 1) {
-            const uint32_t pos = lo + (v & 0xFFFFu);
-            rank = rank_in_bucket(S, lo, hi, S.words[pos], S.sec[pos]);
+            const uint32_t mine = S.tie[e];
+            for (uint32_t y = lo; y < hi; ++y) {
+                const uint32_t ey = S.words[y];
+                const uint32_t ty = S.tie[ey];
+                rank += (ty < mine || (ty == mine && ey < e)) ? 1u : 0u;
+            }
         }
         emit(e, lo + rank);
     }
@@ -320,7 +321,8 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
 // inside one threshold row are interchangeable for the overlap grid, so an element whose whole bucket lies inside one
 // row takes position off[bucket] + arrival without being ranked.  Buckets that contain a row boundary strictly inside
 // are found from the boundaries' side (one binary search over the bucket offsets per threshold, `bounds` = Problem::c1);
-// only their elements (~5 %) get a secondary key and an exact rank.  The result is the exact variant's permutation up
+// only their elements (~5-8 %) get a secondary key and an exact rank, entirely in shared memory: the staged row itself
+// holds the member list of such a bucket until the ranks are known.  The result is the exact variant's permutation up
 // to within-row order; the records it leads to are identical.
 __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const uint32_t *bounds, uint32_t n, int B,
                                     uint64_t seed, uint64_t perm_id, uint32_t stream, uint16_t *stage) {
@@ -351,45 +353,57 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         if (cut[r] != 0xFFFFFFFFu) atomicOr(&S.cnt[cut[r]], 0x80000000u);
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
+    auto lst = [&](uint32_t x) -> uint32_t & { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
+    // placement, 4 elements (one 128-bit word of ba, one 8-byte word of partner slots) per step
     const uint4 *ba4 = reinterpret_cast<const uint4 *>(S.ba);
-    for (uint32_t c = tid; c < n8; c += nt) {
-        const uint4 va = ba4[c], vb = ba4[n8 + c];
-        const uint32_t v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-        // partner slots of the 8 elements of this key block: one 16-byte load (dslot2 is padded to a multiple of 8)
-        const uint4 dsv = *reinterpret_cast<const uint4 *>(P.dslot2 + (size_t)c * 8);
-        const uint32_t dsw[4] = {dsv.x, dsv.y, dsv.z, dsv.w};
+    for (uint32_t u = tid; u < 2 * n8; u += nt) {
+        const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
+        const uint4 va = ba4[u];
+        const uint32_t v[4] = {va.x, va.y, va.z, va.w};
+        const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + e0);  // dslot2 is padded to a multiple of 8
+        const uint32_t dsw[2] = {dsv.x, dsv.y};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t e = c * 8 + q;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t e = e0 + q;
             if (e < n) {
-                const uint32_t w = S.cnt[v[q] >> (32 - B)];
+                const uint32_t b = v[q] >> (32 - B);
+                const uint32_t w = S.cnt[b];
+                const uint32_t pos = (w & kPosMask) + (v[q] & 0xFFFFu);
                 if (!(w >> 31)) {
-                    const uint32_t pos = w + (v[q] & 0xFFFFu);
                     if (pos < P.n1_eff) stage[pos] = (uint16_t)((q & 1) ? (dsw[q >> 1] >> 16) : (dsw[q >> 1] & 0xFFFFu));
                 } else {
-                    S.list[atomicAdd(&S.scan_tmp[32], 1u)] = e;
+                    stage[pos] = (uint16_t)e;  // member list of a boundary bucket (stage holds >= n entries)
+                    lst(atomicAdd(&S.scan_tmp[32], 1u)) = (b << 16) | e;
                 }
             }
         }
     }
     __syncthreads();
-    const uint32_t n_list = S.scan_tmp[32], remmask = (1u << (16 - B)) - 1u;
+    const uint32_t n_list = S.scan_tmp[32];
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t e = S.list[x];
-        const uint32_t v = S.ba[ba_index(e, n8)];
-        const uint32_t pos = (S.cnt[v >> (32 - B)] & kPosMask) + (v & 0xFFFFu);
-        S.words[pos] = (((v >> 16) & remmask) << 16) | e;
-        S.sec[pos] = secondary_key(seed, perm_id, stream, e);
+        const uint32_t e = lst(x) & 0xFFFFu;
+        uint32_t &slot = S.ba[ba_index(e, n8)];
+        slot = tie_word(slot >> 16, secondary_key(seed, perm_id, stream, e), B);
     }
     __syncthreads();
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t e = S.list[x];
-        const uint32_t v = S.ba[ba_index(e, n8)];
-        const uint32_t b = v >> (32 - B);
+        const uint32_t ent = lst(x);
+        const uint32_t e = ent & 0xFFFFu, b = ent >> 16;
         const uint32_t lo = S.cnt[b] & kPosMask, hi = S.cnt[b + 1] & kPosMask;
-        const uint32_t pos = lo + (v & 0xFFFFu);
-        const uint32_t f = lo + rank_in_bucket(S, lo, hi, S.words[pos], S.sec[pos]);
-        if (f < P.n1_eff) stage[f] = P.dslot2[e];
+        const uint32_t mine = S.ba[ba_index(e, n8)];
+        uint32_t rank = 0;
+        for (uint32_t y = lo; y < hi; ++y) {
+            const uint32_t ey = stage[y];
+            const uint32_t ty = S.ba[ba_index(ey, n8)];
+            rank += (ty < mine || (ty == mine && ey < e)) ? 1u : 0u;
+        }
+        lst(x) = ((lo + rank) << 16) | e;
+    }
+    __syncthreads();
+    for (uint32_t x = tid; x < n_list; x += nt) {
+        const uint32_t ent = lst(x);
+        const uint32_t f = ent >> 16;
+        if (f < P.n1_eff) stage[f] = P.dslot2[ent & 0xFFFFu];
     }
     __syncthreads();
 }
@@ -399,19 +413,20 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
                                                                    uint16_t *__restrict__ pb,
                                                                    uint32_t *__restrict__ pairing_out,
                                                                    uint32_t *__restrict__ scratch_base,
-                                                                   int ba_in_scratch) {
+                                                                   int ba_in_scratch, uint32_t list_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const uint32_t nmax8 = (nmax + 7) & ~7u;
     const int Bmax = B1 > B2 ? B1 : B2;
-    // shared: cnt[NB+1] | scan_tmp[33] | pad | stage[pb_stride] u16 | bounds[T1] u32 | order2[n_common] u16 | ba[nmax8] u32
-    // per-CTA global scratch (L2-resident): words[nmax8] | sec[nmax8] | list[nmax8] | ba[nmax8] (when it does not fit)
+    // shared: cnt[NB+1] | scan_tmp[33] | pad | stage[max(pb_stride, nmax8)] u16 | bounds[T1] u32 | order2[n_common] u16 |
+    //         ba[nmax8] u32 (unless in scratch) | list_s[list_cap] u32
+    // per-CTA global scratch (L2-resident): words[nmax8] | tie[nmax8] | list_g[nmax8] | ba[nmax8] (when it does not fit)
     SortShared S;
     S.cnt = reinterpret_cast<uint32_t *>(smem_raw);
     S.scan_tmp = S.cnt + (1u << Bmax) + 1;
     size_t off = (((size_t)(1u << Bmax) + 1 + 33) * 4 + 15) & ~(size_t)15;
-    uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + off);  // pb_stride is a multiple of 256: 16 B aligned end
-    off += (size_t)P.pb_stride * 2;
+    uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + off);
+    off += (size_t)(P.pb_stride > nmax8 ? P.pb_stride : nmax8) * 2;  // both are multiples of 8 entries: 16 B aligned
     uint32_t *bounds = reinterpret_cast<uint32_t *>(smem_raw + off);
     off += (((size_t)P.T1 * 4) + 15) & ~(size_t)15;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
@@ -419,9 +434,16 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     if (!identical) off += (((size_t)P.n_common * 2) + 15) & ~(size_t)15;
     uint32_t *scratch = scratch_base + (size_t)blockIdx.x * 4 * nmax8;
     S.words = scratch;
-    S.sec = scratch + nmax8;
-    S.list = scratch + 2 * (size_t)nmax8;
-    S.ba = ba_in_scratch ? scratch + 3 * (size_t)nmax8 : reinterpret_cast<uint32_t *>(smem_raw + off);
+    S.tie = scratch + nmax8;
+    S.list_g = scratch + 2 * (size_t)nmax8;
+    if (ba_in_scratch) {
+        S.ba = scratch + 3 * (size_t)nmax8;
+    } else {
+        S.ba = reinterpret_cast<uint32_t *>(smem_raw + off);
+        off += (size_t)nmax8 * 4;
+    }
+    S.list_s = reinterpret_cast<uint32_t *>(smem_raw + off);
+    S.list_cap = list_cap;
     for (uint32_t x = threadIdx.x; x < (uint32_t)P.T1; x += blockDim.x) bounds[x] = P.c1[x];
     __syncthreads();
     const bool rowwise = identical && pairing_out == nullptr;
@@ -1213,17 +1235,18 @@ cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *
     return cudaGetLastError();
 }
 
-// shared-memory bytes of the pairing kernel; ba_in_smem = false moves the n x 4 B (key16 | arrival) array to the
-// per-CTA global scratch (long lists)
+// shared-memory bytes of the pairing kernel without the boundary list; ba_in_smem = false moves the n x 4 B
+// (key16 | arrival) array to the per-CTA global scratch (long lists)
 size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool ba_in_smem) {
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+    const uint32_t nmax8 = (nmax + 7) & ~7u;
     const int Bmax = B1 > B2 ? B1 : B2;
     size_t b = (((size_t)(1u << Bmax) + 1 + 33) * 4 + 15) & ~(size_t)15;
-    b += (size_t)P.pb_stride * 2;
+    b += (size_t)(P.pb_stride > nmax8 ? P.pb_stride : nmax8) * 2;
     b += (((size_t)P.T1 * 4) + 15) & ~(size_t)15;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);
     if (!identical) b += (((size_t)P.n_common * 2) + 15) & ~(size_t)15;
-    if (ba_in_smem) b += (size_t)((nmax + 7) & ~7u) * 4;
+    if (ba_in_smem) b += (size_t)nmax8 * 4;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -1246,12 +1269,16 @@ cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id
                               uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit, int grid, cudaStream_t st) {
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
     const bool ba_in_smem = sigma_smem_bytes(P, B1, B2, true) <= smem_limit;
-    const size_t smem = sigma_smem_bytes(P, B1, B2, ba_in_smem);
-    if (smem > smem_limit || !scratch) return cudaErrorInvalidValue;
+    const size_t base = sigma_smem_bytes(P, B1, B2, ba_in_smem);
+    if (base > smem_limit || !scratch) return cudaErrorInvalidValue;
+    // whatever shared memory is left holds the boundary-bucket list (it spills to the global scratch beyond that)
+    const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+    const size_t list_cap = std::min<size_t>((smem_limit - base) / 4 & ~(size_t)3, (nmax + 7) & ~7u);
+    const size_t smem = base + list_cap * 4;
     cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
     sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, scratch,
-                                                        ba_in_smem ? 0 : 1);
+                                                        ba_in_smem ? 0 : 1, (uint32_t)list_cap);
     return cudaGetLastError();
 }
 

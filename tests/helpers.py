@@ -158,8 +158,13 @@ def device_keys16(n, seed, perm_id, stream):
 
 def expected_pairing_identical(n, seed, perm_id):
     """pos2_of_pos1 for identical gene sets: list-1 position f is paired with the list-2 position whose key has rank f.
-    Order = (16-bit primary key, 32-bit secondary Philox key (stream + 8), index)."""
+    Order = (16-bit primary key, top 16 + B bits of the 32-bit secondary Philox key (stream + 8), index), B = bucket bits
+    of the kernel (the tie-break word packs the key16 bits below the bucket bits and those secondary bits into 32 bits)."""
+    lg = 0
+    while (1 << lg) < n:
+        lg += 1
+    B = min(14, max(1, lg - 1))
     key = device_keys16(n, seed, perm_id, 0)
-    sec = device_keys(n, seed, perm_id, 8)
+    sec = device_keys(n, seed, perm_id, 8) >> np.uint64(16 - B)
     order = np.lexsort((np.arange(n), sec, key))
     return order.astype(np.uint32)
