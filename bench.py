@@ -201,6 +201,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # stdout must carry exactly ONE line (the JSON): native libraries write banners to fd 1 (NCCL prints its version on the
+    # first communicator), so fd 1 points at stderr until the line is printed through a saved copy of the real stdout
+    real_stdout = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -382,7 +388,7 @@ def main():
             "stats": {k: st[k] for k in ("tasks_fast", "tasks_full", "candidates", "level2_cells", "refined_cells")},
             "unpermuted": {"rank1": int(unperm["rank1"]), "rank2": int(unperm["rank2"]), "pvalue": float(unperm["pvalue"]), "empirical_pvalue": emp},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
