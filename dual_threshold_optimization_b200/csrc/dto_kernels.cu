@@ -827,102 +827,62 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
     __syncwarp();
 }
 
+// State of one permutation's row loop that survives a trip through the rare path (kept in local memory between calls of
+// scan_rows, in registers inside it).
+template <int CH>
+struct RowState {
+    uint32_t kcur2[CH / 2];  // overlap counts of this lane's CH columns, two 16-bit counts per word (k <= 65534)
+    uint32_t koff2;          // overlap contributed by the lanes to the left, in both halves
+    uint32_t qn;             // warp-uniform copy of the queue length (refreshed only after rows that pushed something)
+    uint32_t lo, cbase;      // next list-1 position; oldest resident chunk of the partner-slot ring
+    int i, level;            // next row; screen level
+};
+
+__device__ __forceinline__ void ring_issue_chunk(const uint16_t *row, uint32_t n_chunks, uint32_t ring_addr, int lane,
+                                                 uint32_t c) {
+    if (c < n_chunks) {
+        const uint16_t *src = row + (size_t)c * kChunk + lane * 4;
+        const uint32_t dst = ring_addr + ((c & 3u) * kChunk + lane * 4) * 2;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// The row loop of one permutation, from row st.i until the screen queue holds a full chunk (st.qn >= 32) or the last
+// row is done.  A function of its own ON PURPOSE: ptxas allocates registers per function, so the loop keeps its 2 x CH/2
+// words of column state in registers no matter what the per-task prologue and the rare path of the kernel need.
 template <int CH, bool SWAR>
-__global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : kScanCtasPerSm)
-scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
-            dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
-            unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats) {
+__device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const uint16_t *__restrict__ row,
+                                       unsigned char *wbase, const uint32_t *s_c1) {
     using L = ScanLayout<CH>;
     constexpr int CHP = L::CHP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *s_c1 = reinterpret_cast<uint32_t *>(smem_raw);  // [T1] shared by the CTA
-    const size_t c1_bytes = ((size_t)P.T1 * 4 + 15) & ~(size_t)15;
-    unsigned char *wbase = smem_raw + c1_bytes + (size_t)warp * L::per_warp;
+    constexpr int NP = CH / 2;
+    const int lane = threadIdx.x & 31;
     uint32_t *D = reinterpret_cast<uint32_t *>(wbase);
     uint32_t *Qij = reinterpret_cast<uint32_t *>(wbase + L::d_bytes);
     uint16_t *Qk = reinterpret_cast<uint16_t *>(Qij + L::QCAP);
     uint32_t *qcnt = reinterpret_cast<uint32_t *>(wbase + L::d_bytes + L::q_bytes);
-    Cand *cand = reinterpret_cast<Cand *>(wbase + L::d_bytes + L::q_bytes + 16);
-    uint16_t *ring = reinterpret_cast<uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
+    const uint16_t *ring = reinterpret_cast<const uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
-
-    for (int x = threadIdx.x; x < P.T1; x += blockDim.x) s_c1[x] = P.c1[x];
-    __syncthreads();
-
-    // dynamic scheduling: permutations differ in cost (how many cells pass the screen)
-    for (;;) {
-        int task = 0;
-        if (lane == 0) task = (int)atomicAdd(reinterpret_cast<unsigned int *>(&counters[7]), 1u);
-        task = __shfl_sync(kFull, task, 0);
-        if (task >= n_tasks) break;
-        const uint16_t *__restrict__ row = pb + (size_t)task * P.pb_stride;
-        const long long t_begin = task_stats ? clock64() : 0;
-        for (int x = lane; x < 32 * CHP; x += 32) D[x] = 0;
-        if (lane == 0) *qcnt = 0;
-        __syncwarp();
-
-        Rare R;
-        R.theta = CUDART_INF;
-        R.ex.best.p = CUDART_INF;
-        R.ex.best.k = 0;
-        R.ex.best.ij = 0xFFFFFFFFu;
-        R.ex.near = false;
-        R.zero.p = 0.0;
-        R.zero.k = 0;
-        R.zero.ij = 0xFFFFFFFFu;
-        R.ncand = 0;
-        R.n_level2 = R.n_eval = R.n_refine = 0;
-        R.s_c1 = s_c1;
-        R.Qij = Qij;
-        R.Qk = Qk;
-        R.qcnt = qcnt;
-        R.cand = cand;
-        R.lane = lane;
-
-        // overlap counts of this lane's CH columns, two 16-bit counts per register (k <= 65534 by the list-size limit)
-        constexpr int NP = CH / 2;
-        uint32_t kcur2[NP];
+    const uint32_t n_chunks = P.pb_stride / kChunk;
+    uint32_t kcur2[NP];
 #pragma unroll
-        for (int q = 0; q < NP; ++q) kcur2[q] = 0;
-        uint32_t koff2 = 0;  // overlap contributed by the lanes to the left, in both halves
-        uint32_t qn = 0;     // warp-uniform copy of *qcnt (refreshed only after rows that pushed something)
-        int level = 0;
-
-        // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
-        // lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)
-        const uint32_t n_chunks = P.pb_stride / kChunk;
-        auto issue_chunk = [&](uint32_t c) {
-            if (c < n_chunks) {
-                const uint16_t *src = row + (size_t)c * kChunk + lane * 4;
-                const uint32_t dst = ring_addr + ((c & 3u) * kChunk + lane * 4) * 2;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        issue_chunk(0);
-        issue_chunk(1);
+    for (int q = 0; q < NP; ++q) kcur2[q] = st.kcur2[q];
+    uint32_t koff2 = st.koff2, qn = st.qn, lo = st.lo, cbase = st.cbase;
+    int i = st.i;
+    const int level = st.level;
+    auto advance_ring = [&]() {  // chunk cbase is consumed: cbase+2 must have landed, refill the freed slot
+        ++cbase;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        issue_chunk(2);
-        uint32_t cbase = 0, lo = 0;
-        auto advance_ring = [&]() {  // chunk cbase is consumed: cbase+2 must have landed, refill the freed slot
-            ++cbase;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            issue_chunk(cbase + 2);
-        };
-        // this lane's words of the current row of critical overlaps (level `level`, row i), advanced row by row
-        auto kcrit_row = [&](int lvl, int r) {
-            return reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)lvl * P.T1 + r) * P.T2pad) + lane;
-        };
-        const uint32_t *__restrict__ kr = kcrit_row(0, 0);
-        const uint32_t kr_step = (uint32_t)P.T2pad >> 1;  // 32-bit words per row
-        uint4 *D4 = reinterpret_cast<uint4 *>(D + lane * CHP);  // this lane's column pairs, 4 per 128-bit vector
-        // The row loop is call-free: when the queue holds a full chunk it BREAKS to the (out-of-line) drain and
-        // re-enters, so the column state is only saved/restored around that rare call, never inside the loop.
-        int i = 0;
-        while (i < P.T1) {
+        ring_issue_chunk(row, n_chunks, ring_addr, lane, cbase + 2);
+    };
+    // this lane's words of the current row of critical overlaps (level `level`, row i), advanced row by row
+    const uint32_t *__restrict__ kr =
+        reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
+    const uint32_t kr_step = (uint32_t)P.T2pad >> 1;  // 32-bit words per row
+    uint4 *D4 = reinterpret_cast<uint4 *>(D + lane * CHP);  // this lane's column pairs, 4 per 128-bit vector
+    {
         for (; i < P.T1; ++i) {
             const uint32_t hi = s_c1[i];
             // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
@@ -1037,13 +997,93 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
                 break;
             }
         }
-        if (qn >= 32) {
-            level = drain_queue(P, R, false, level);
-            kr = kcrit_row(level, i);
-            __syncwarp();
-            qn = *qcnt;
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) st.kcur2[q] = kcur2[q];
+    st.koff2 = koff2;
+    st.qn = qn;
+    st.lo = lo;
+    st.cbase = cbase;
+    st.i = i;
+}
+
+template <int CH, bool SWAR>
+__global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : kScanCtasPerSm)
+scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
+            dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
+            unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats) {
+    using L = ScanLayout<CH>;
+    constexpr int CHP = L::CHP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *s_c1 = reinterpret_cast<uint32_t *>(smem_raw);  // [T1] shared by the CTA
+    const size_t c1_bytes = ((size_t)P.T1 * 4 + 15) & ~(size_t)15;
+    unsigned char *wbase = smem_raw + c1_bytes + (size_t)warp * L::per_warp;
+    uint32_t *D = reinterpret_cast<uint32_t *>(wbase);
+    uint32_t *Qij = reinterpret_cast<uint32_t *>(wbase + L::d_bytes);
+    uint16_t *Qk = reinterpret_cast<uint16_t *>(Qij + L::QCAP);
+    uint32_t *qcnt = reinterpret_cast<uint32_t *>(wbase + L::d_bytes + L::q_bytes);
+    Cand *cand = reinterpret_cast<Cand *>(wbase + L::d_bytes + L::q_bytes + 16);
+    uint16_t *ring = reinterpret_cast<uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
+
+    for (int x = threadIdx.x; x < P.T1; x += blockDim.x) s_c1[x] = P.c1[x];
+    __syncthreads();
+
+    // dynamic scheduling: permutations differ in cost (how many cells pass the screen)
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = (int)atomicAdd(reinterpret_cast<unsigned int *>(&counters[7]), 1u);
+        task = __shfl_sync(kFull, task, 0);
+        if (task >= n_tasks) break;
+        const uint16_t *__restrict__ row = pb + (size_t)task * P.pb_stride;
+        const long long t_begin = task_stats ? clock64() : 0;
+        for (int x = lane; x < 32 * CHP; x += 32) D[x] = 0;
+        if (lane == 0) *qcnt = 0;
+        __syncwarp();
+
+        Rare R;
+        R.theta = CUDART_INF;
+        R.ex.best.p = CUDART_INF;
+        R.ex.best.k = 0;
+        R.ex.best.ij = 0xFFFFFFFFu;
+        R.ex.near = false;
+        R.zero.p = 0.0;
+        R.zero.k = 0;
+        R.zero.ij = 0xFFFFFFFFu;
+        R.ncand = 0;
+        R.n_level2 = R.n_eval = R.n_refine = 0;
+        R.s_c1 = s_c1;
+        R.Qij = Qij;
+        R.Qk = Qk;
+        R.qcnt = qcnt;
+        R.cand = cand;
+        R.lane = lane;
+
+        RowState<CH> st;
+#pragma unroll
+        for (int q = 0; q < CH / 2; ++q) st.kcur2[q] = 0;
+        st.koff2 = st.qn = st.lo = st.cbase = 0;
+        st.i = st.level = 0;
+        // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
+        // lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)
+        const uint32_t n_chunks = P.pb_stride / kChunk;
+        ring_issue_chunk(row, n_chunks, ring_addr, lane, 0);
+        ring_issue_chunk(row, n_chunks, ring_addr, lane, 1);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        ring_issue_chunk(row, n_chunks, ring_addr, lane, 2);
+        // The row loop lives in scan_rows and is call-free: when the queue holds a full chunk it returns to the
+        // (out-of-line) drain and is re-entered, so the column state is only saved/restored around that rare trip.
+        while (st.i < P.T1) {
+            scan_rows<CH, SWAR>(P, st, row, wbase, s_c1);
+            if (st.qn >= 32) {
+                st.level = drain_queue(P, R, false, st.level);
+                __syncwarp();
+                st.qn = *qcnt;
+            }
         }
-        }
+        const int level = st.level;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         finish_task(P, R, task, level, record_flags, out, status, counters, task_stats, t_begin);
     }
