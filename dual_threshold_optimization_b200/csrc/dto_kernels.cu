@@ -881,9 +881,10 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
     const uint32_t *__restrict__ kr =
         reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
     const uint32_t kr_step = (uint32_t)P.T2pad >> 1;  // 32-bit words per row
+    const int T1 = P.T1;  // P lives behind a generic pointer here: read the loop bound once, not once per row
     uint4 *D4 = reinterpret_cast<uint4 *>(D + lane * CHP);  // this lane's column pairs, 4 per 128-bit vector
     {
-        for (; i < P.T1; ++i) {
+        for (; i < T1; ++i) {
             const uint32_t hi = s_c1[i];
             // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
             // the scatter)
