@@ -145,7 +145,9 @@ int dto_b200_last_batch_task_stats(dto_b200_ctx *ctx, uint32_t *out, size_t max_
 int dto_b200_table_logp(dto_b200_ctx *ctx, const uint32_t *row, const uint32_t *col, const uint32_t *k, size_t count,
                         double *logp_out);
 
-/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" and "packed_screen" (before set_problem), "task_stats" */
+/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" and "packed_screen" (before set_problem),
+ * "task_stats", "table_cache" (1 = reuse the screen / log-p tables of the previous problem when population and set sizes
+ * per threshold are equal, the default; 0 = always rebuild) */
 int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value);
 
 /* micro-probes used by bench.py for roofline denominators (measured live, not assumed) */
