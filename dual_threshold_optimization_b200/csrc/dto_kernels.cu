@@ -353,41 +353,66 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         if (cut[r] != 0xFFFFFFFFu) atomicOr(&S.cnt[cut[r]], 0x80000000u);
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
-    auto lst = [&](uint32_t x) -> uint32_t & { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
-    // placement, 4 elements (one 128-bit word of ba, one 8-byte word of partner slots) per step
+    // the boundary list: first list_cap entries in shared memory, the rest in the global scratch (two explicit branches
+    // so that each side is a plain shared / global access, not a generic one)
+    auto lst_put = [&](uint32_t x, uint32_t v) {
+        if (x < S.list_cap) S.list_s[x] = v;
+        else S.list_g[x] = v;
+    };
+    auto lst_get = [&](uint32_t x) -> uint32_t { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
+    // placement, 4 elements (one 128-bit word of ba, one 8-byte word of partner slots) per step, branch-free: an element
+    // of a boundary bucket stores its own index (the staged row doubles as the member list of such a bucket; it holds
+    // >= n entries), any other element its partner slot.  The boundary elements of a warp's step are appended to the
+    // list with one warp-aggregated atomic.
     const uint4 *ba4 = reinterpret_cast<const uint4 *>(S.ba);
-    for (uint32_t u = tid; u < 2 * n8; u += nt) {
-        const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
-        const uint4 va = ba4[u];
-        const uint32_t v[4] = {va.x, va.y, va.z, va.w};
-        const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + e0);  // dslot2 is padded to a multiple of 8
-        const uint32_t dsw[2] = {dsv.x, dsv.y};
+    const uint32_t lane = tid & 31u;
+    const uint32_t steps = 2 * n8, steps_warp = (steps + 31u) & ~31u;  // whole warps stay in the loop (votes, shuffles)
+    for (uint32_t u = tid; u < steps_warp; u += nt) {
+        uint32_t cutmask = 0, ent[4] = {0u, 0u, 0u, 0u};
+        if (u < steps) {
+            const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
+            const uint4 va = ba4[u];
+            const uint32_t v[4] = {va.x, va.y, va.z, va.w};
+            const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + e0);  // dslot2 is padded to a multiple of 8
+            const uint32_t ds[4] = {dsv.x & 0xFFFFu, dsv.x >> 16, dsv.y & 0xFFFFu, dsv.y >> 16};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t e = e0 + q;
-            if (e < n) {
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t e = e0 + q;
                 const uint32_t b = v[q] >> (32 - B);
                 const uint32_t w = S.cnt[b];
                 const uint32_t pos = (w & kPosMask) + (v[q] & 0xFFFFu);
-                if (!(w >> 31)) {
-                    if (pos < P.n1_eff) stage[pos] = (uint16_t)((q & 1) ? (dsw[q >> 1] >> 16) : (dsw[q >> 1] & 0xFFFFu));
-                } else {
-                    stage[pos] = (uint16_t)e;  // member list of a boundary bucket (stage holds >= n entries)
-                    lst(atomicAdd(&S.scan_tmp[32], 1u)) = (b << 16) | e;
-                }
+                const bool cutb = (w >> 31) != 0u;
+                if (e < n && (cutb || pos < P.n1_eff)) stage[pos] = (uint16_t)(cutb ? e : ds[q]);
+                ent[q] = (b << 16) | e;
+                if (e < n && cutb) cutmask |= 1u << q;
             }
+        }
+        if (__any_sync(kFull, cutmask != 0u)) {
+            const uint32_t nf = __popc(cutmask);
+            uint32_t inc = nf;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, inc, o);
+                if (lane >= (uint32_t)o) inc += t;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(&S.scan_tmp[32], inc);
+            base = __shfl_sync(kFull, base, 31) + inc - nf;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (cutmask & (1u << q)) lst_put(base + __popc(cutmask & ((1u << q) - 1u)), ent[q]);
         }
     }
     __syncthreads();
     const uint32_t n_list = S.scan_tmp[32];
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t e = lst(x) & 0xFFFFu;
+        const uint32_t e = lst_get(x) & 0xFFFFu;
         uint32_t &slot = S.ba[ba_index(e, n8)];
         slot = tie_word(slot >> 16, secondary_key(seed, perm_id, stream, e), B);
     }
     __syncthreads();
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t ent = lst(x);
+        const uint32_t ent = lst_get(x);
         const uint32_t e = ent & 0xFFFFu, b = ent >> 16;
         const uint32_t lo = S.cnt[b] & kPosMask, hi = S.cnt[b + 1] & kPosMask;
         const uint32_t mine = S.ba[ba_index(e, n8)];
@@ -397,23 +422,24 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
             const uint32_t ty = S.ba[ba_index(ey, n8)];
             rank += (ty < mine || (ty == mine && ey < e)) ? 1u : 0u;
         }
-        lst(x) = ((lo + rank) << 16) | e;
+        lst_put(x, ((lo + rank) << 16) | e);
     }
     __syncthreads();
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t ent = lst(x);
+        const uint32_t ent = lst_get(x);
         const uint32_t f = ent >> 16;
         if (f < P.n1_eff) stage[f] = P.dslot2[ent & 0xFFFFu];
     }
     __syncthreads();
 }
 
+template <bool BA_IN_SCRATCH>
 __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed,
                                                                    uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
                                                                    uint32_t *__restrict__ pairing_out,
                                                                    uint32_t *__restrict__ scratch_base,
-                                                                   int ba_in_scratch, uint32_t list_cap) {
+                                                                   uint32_t list_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const uint32_t nmax8 = (nmax + 7) & ~7u;
@@ -436,7 +462,7 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     S.words = scratch;
     S.tie = scratch + nmax8;
     S.list_g = scratch + 2 * (size_t)nmax8;
-    if (ba_in_scratch) {
+    if constexpr (BA_IN_SCRATCH) {  // a template parameter so that the shared-memory case compiles to LDS/STS, not generic
         S.ba = scratch + 3 * (size_t)nmax8;
     } else {
         S.ba = reinterpret_cast<uint32_t *>(smem_raw + off);
@@ -1316,10 +1342,10 @@ cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const size_t list_cap = std::min<size_t>((smem_limit - base) / 4 & ~(size_t)3, (nmax + 7) & ~7u);
     const size_t smem = base + list_cap * 4;
-    cudaError_t e = cudaFuncSetAttribute(sigma_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
+    auto kern = ba_in_smem ? sigma_sort_kernel<false> : sigma_sort_kernel<true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
-    sigma_sort_kernel<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, scratch,
-                                                        ba_in_smem ? 0 : 1, (uint32_t)list_cap);
+    kern<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, scratch, (uint32_t)list_cap);
     return cudaGetLastError();
 }
 
