@@ -208,17 +208,15 @@ __device__ void block_exclusive_scan_t(uint32_t *a, uint32_t len, uint32_t *tmp)
     }
     if (lane == 31) tmp[w] = inc;
     __syncthreads();
-    if (w == 0) {
-        uint32_t v = (lane < (nt >> 5)) ? tmp[lane] : 0, s = v;
+    // every warp scans the (at most 32) warp totals itself: one barrier less than handing the job to warp 0
+    uint32_t wv = (lane < (nt >> 5)) ? tmp[lane] : 0, ws = wv;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(kFull, s, o);
-            if (lane >= (uint32_t)o) s += u;
-        }
-        tmp[lane] = s - v;  // exclusive warp offsets
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(kFull, ws, o);
+        if (lane >= (uint32_t)o) ws += u;
     }
-    __syncthreads();
-    uint32_t run = tmp[w] + inc - sum;
+    const uint32_t woff = __shfl_sync(kFull, ws - wv, (int)w);  // exclusive offset of this warp
+    uint32_t run = woff + inc - sum;
     if (V > 0) {
         uint4 *a4 = reinterpret_cast<uint4 *>(a + b);
 #pragma unroll
@@ -252,12 +250,20 @@ __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
 
 // Pass 1 + scan, shared by both variants: on return cnt[b] = first position of bucket b (cnt[NB] = n) and ba holds
 // (key16 << 16 | arrival) of every element.
-__device__ void block_bucket_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id, uint32_t stream) {
+__device__ __forceinline__ void block_zero_counters(const SortShared &S, int B) {
+    for (uint32_t x = threadIdx.x; x <= (1u << B); x += blockDim.x) S.cnt[x] = 0;
+    if (threadIdx.x == 0) S.scan_tmp[32] = 0;
+}
+
+// pre_zeroed: the caller cleared the counters in an earlier phase that a barrier already closed
+__device__ void block_bucket_keys(const SortShared &S, uint32_t n, int B, uint64_t seed, uint64_t perm_id, uint32_t stream,
+                                  bool pre_zeroed = false) {
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    for (uint32_t x = tid; x <= NB; x += nt) S.cnt[x] = 0;
-    if (tid == 0) S.scan_tmp[32] = 0;
-    __syncthreads();
+    if (!pre_zeroed) {
+        block_zero_counters(S, B);
+        __syncthreads();
+    }
     const uint32_t n8 = (n + 7) >> 3;
     uint4 *ba4 = reinterpret_cast<uint4 *>(S.ba);
     for (uint32_t c = tid; c < n8; c += nt) {
@@ -326,7 +332,7 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
 // to within-row order; the records it leads to are identical.
 __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const uint32_t *bounds, uint32_t n, int B,
                                     uint64_t seed, uint64_t perm_id, uint32_t stream, uint16_t *stage) {
-    block_bucket_keys(S, n, B, seed, perm_id, stream);
+    block_bucket_keys(S, n, B, seed, perm_id, stream, true);  // the kernel zeroes the counters during the copy-out
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     // flag the buckets a row boundary p cuts (off[b] < p < off[b+1]); T1 <= 2048 = 2 boundaries per thread
@@ -430,6 +436,9 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         const uint32_t f = ent >> 16;
         if (f < P.n1_eff) stage[f] = P.dslot2[ent & 0xFFFFu];
     }
+    // positions past the last threshold carry no partner (disjoint from the writes above; member lists that reached into
+    // this range were consumed before the previous barrier)
+    for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
     __syncthreads();
 }
 
@@ -474,13 +483,16 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     __syncthreads();
     const bool rowwise = identical && pairing_out == nullptr;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    if (rowwise) {
+        block_zero_counters(S, B2);
+        __syncthreads();
+    }
 
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const uint64_t perm_id = first_id + (uint64_t)t;
         uint16_t *dst = pb + (size_t)t * P.pb_stride;
         if (rowwise) {
             block_place_rowwise(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
-            for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
         } else if (identical) {
             // element = list-2 position e, rank f = the list-1 position it is paired with
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
@@ -488,6 +500,7 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
                 if (pairing_out) pairing_out[(size_t)t * P.n1 + f] = e;
             });
             for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
+            __syncthreads();
         } else {
             // uniform random partial injection: the n_common lowest-keyed positions of each list, matched by rank
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 1u, [&](uint32_t e, uint32_t f) {
@@ -501,12 +514,14 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
                 if (pairing_out) pairing_out[(size_t)t * P.n1 + e] = partner;
             });
             for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
+            __syncthreads();
         }
-        __syncthreads();
-        // coalesced copy-out, 8 bytes per thread (pb_stride is a multiple of 256, rows are 512 B aligned)
+        // coalesced copy-out, 8 bytes per thread (pb_stride is a multiple of 256, rows are 512 B aligned); the row-wise
+        // variant clears its bucket counters for the next permutation in the same phase
         const uint2 *s2 = reinterpret_cast<const uint2 *>(stage);
         uint2 *d2 = reinterpret_cast<uint2 *>(dst);
         for (uint32_t x = tid; x < P.pb_stride / 4; x += nt) d2[x] = s2[x];
+        if (rowwise) block_zero_counters(S, B2);
         __syncthreads();
     }
 }
