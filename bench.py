@@ -288,7 +288,7 @@ def main():
     e2e_records = np.zeros(P + 1, dtype=RECORD_DTYPE)  # host result buffer of one step: [unpermuted, P permuted]
 
     def e2e_step(step_idx):
-        eng.load_lists(l1, l2, population)          # H2D: ranks, thresholds, slot map (+ tables rebuilt on the device)
+        eng.load_lists(l1, l2, population)          # H2D: ranks, thresholds, slot map (screen tables: cache hit, same set sizes)
         e2e_records[0] = eng.run_unpermuted()        # D2H: the unpermuted record
         eng.run_permuted_philox(PHILOX_SEED, (step_idx * world + rank) * P, P, out=e2e_records[1:])  # D2H: P records
         return empirical_pvalue_struct(e2e_records).empirical_pvalue   # host epilogue (empirical p, FDR)
