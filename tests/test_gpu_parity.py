@@ -110,12 +110,14 @@ def test_permuted_host_indices_match_oracle(engine, name, P):
         check_grid(engine, o1, o2, N, slot, p1[t], p2[t])
 
 
-@pytest.mark.parametrize("N,P,sigma", [(6000, 6, 0.25), (6000, 6, None), (20000, 3, None)])
-def test_baseline_sizes_match_oracle(engine, N, P, sigma):
-    """configs C2 / C3 of BASELINE.json at full feature counts (few tasks: the oracle needs ~seconds per task)."""
-    ids1, r1, ids2, r2 = H.synthetic_pair(N, N, sigma)
+@pytest.mark.parametrize("N,P,sigma,ties", [(6000, 6, 0.25, 0.0), (6000, 6, None, 0.0), (20000, 3, None, 0.0), (6000, 4, 0.25, 0.05)])
+def test_baseline_sizes_match_oracle(engine, N, P, sigma, ties):
+    """configs C2 / C3 of BASELINE.json at full feature counts (few tasks: the oracle needs ~seconds per task), plus the
+    tied variant of SURVEY 8(d): 5 % of the features collapsed into tie groups."""
+    ids1, r1, ids2, r2 = H.synthetic_pair(N, N, sigma, tied_frac=ties)
     o1, o2, pop, slot = load(engine, ids1, r1, ids2, r2)
-    assert (o1.thresholds.size, o2.thresholds.size) == ({6000: 469, 20000: 589}[N],) * 2
+    if not ties:
+        assert (o1.thresholds.size, o2.thresholds.size) == ({6000: 469, 20000: 589}[N],) * 2
     lf = O.ln_factorial_table(pop)
     rec = engine.run_unpermuted()
     H.assert_record_matches(rec, O.grid_int(o1, o2, pop, slot, lf=lf, want_overlap=False, want_p=False).best)
