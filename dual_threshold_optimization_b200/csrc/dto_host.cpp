@@ -27,6 +27,11 @@ struct dto_b200_ranked_list {
     std::vector<uint32_t> ranks;       // ascending
     std::vector<uint32_t> thresholds;  // src/collections/ranked.rs:359-375
     uint64_t uid = 0;                  // unique per created list (lists are immutable after creation)
+    // id index built once at creation: 64-bit hash per id and an open-addressing table of positions, so that joining
+    // two lists (the integer form of intersect_genes) is one flat probe per id instead of a string hash map per pair
+    std::vector<uint64_t> id_hash;
+    std::vector<int32_t> id_table;     // size = power of two >= 2 n; -1 = empty
+    int32_t dup_index = -1;            // position of the first id that repeats an earlier one (-1: all distinct)
     // memo of the last string-id -> slot canonicalisation against another list (a pure function of the two immutable
     // lists); guarded by a mutex because one list may be loaded into several contexts from several threads
     mutable std::mutex memo_mu;
@@ -41,6 +46,54 @@ struct dto_b200_feature_list {
 namespace {
 
 std::atomic<uint64_t> g_next_list_uid{1};
+
+inline uint64_t hash_id(const std::string &s) {  // FNV-1a, finalised so that the low bits are well mixed
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : s) h = (h ^ c) * 1099511628211ull;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    return h;
+}
+
+void build_id_index(dto_b200_ranked_list *l) {
+    const size_t n = l->ids.size();
+    size_t cap = 16;
+    while (cap < 2 * n) cap <<= 1;
+    l->id_hash.resize(n);
+    l->id_table.assign(cap, -1);
+    l->dup_index = -1;
+    for (size_t j = 0; j < n; ++j) {
+        const uint64_t h = hash_id(l->ids[j]);
+        l->id_hash[j] = h;
+        size_t x = (size_t)h & (cap - 1);
+        bool dup = false;
+        while (l->id_table[x] >= 0) {
+            const int32_t o = l->id_table[x];
+            if (l->id_hash[(size_t)o] == h && l->ids[(size_t)o] == l->ids[j]) {
+                dup = true;
+                break;
+            }
+            x = (x + 1) & (cap - 1);
+        }
+        if (dup) {
+            if (l->dup_index < 0) l->dup_index = (int32_t)j;
+        } else {
+            l->id_table[x] = (int32_t)j;
+        }
+    }
+}
+
+inline int32_t find_id(const dto_b200_ranked_list *l, const std::string &id, uint64_t h) {
+    const size_t cap = l->id_table.size();
+    size_t x = (size_t)h & (cap - 1);
+    while (l->id_table[x] >= 0) {
+        const int32_t o = l->id_table[x];
+        if (l->id_hash[(size_t)o] == h && l->ids[(size_t)o] == id) return o;
+        x = (x + 1) & (cap - 1);
+    }
+    return -1;
+}
 
 std::string trim_ws(const std::string &s) {
     size_t b = 0, e = s.size();
@@ -141,6 +194,7 @@ int dto_b200_ranked_list_from(const char *const *ids, const uint32_t *ranks, siz
         l->ranks.push_back(ranks[o]);
     }
     generate_thresholds(l->ranks, l->thresholds);
+    build_id_index(l);
     *out = l;
     return DTO_B200_OK;
 }
@@ -217,9 +271,8 @@ int dto_b200_compute_population_size(const dto_b200_ranked_list *l1, const dto_b
                                      const dto_b200_feature_list *background, uint64_t *population_out) {
     if (!l1 || !l2 || !population_out) return fail(DTO_B200_ERR_INVALID, "null argument");
     if (!background) {
-        std::unordered_set<std::string> s2(l2->ids.begin(), l2->ids.end());
         size_t inter = 0;  // FeatureList::intersect keeps list-1 items whose id is in list 2 (feature_list.rs:278-286)
-        for (auto &g : l1->ids) inter += s2.count(g);
+        for (size_t a = 0; a < l1->ids.size(); ++a) inter += find_id(l2, l1->ids[a], l1->id_hash[a]) >= 0 ? 1 : 0;
         if (inter != l1->ids.size() || inter != l2->ids.size())
             return fail(DTO_B200_ERR_PANIC, "If no background is provided, the feature lists must have identical genes.");
         *population_out = inter;
@@ -257,20 +310,14 @@ int dto_b200_load_lists(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const
         if (l1->memo_partner_uid == l2->uid && l1->memo_slot.size() == l1->ids.size()) slot = l1->memo_slot;
     }
     if (slot.size() != l1->ids.size() || l1->ids.empty()) {
-        std::unordered_map<std::string, int32_t> pos2;
-        pos2.reserve(l2->ids.size() * 2);
-        for (size_t j = 0; j < l2->ids.size(); ++j)
-            if (!pos2.emplace(l2->ids[j], (int32_t)j).second)
-                return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list", l2->ids[j].c_str());
-        std::unordered_set<std::string> seen1;
-        seen1.reserve(l1->ids.size() * 2);
+        if (l2->dup_index >= 0)
+            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list",
+                        l2->ids[(size_t)l2->dup_index].c_str());
+        if (l1->dup_index >= 0)
+            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list",
+                        l1->ids[(size_t)l1->dup_index].c_str());
         slot.assign(l1->ids.size(), -1);
-        for (size_t a = 0; a < l1->ids.size(); ++a) {
-            if (!seen1.insert(l1->ids[a]).second)
-                return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list", l1->ids[a].c_str());
-            auto it = pos2.find(l1->ids[a]);
-            if (it != pos2.end()) slot[a] = it->second;
-        }
+        for (size_t a = 0; a < l1->ids.size(); ++a) slot[a] = find_id(l2, l1->ids[a], l1->id_hash[a]);
         std::lock_guard<std::mutex> lock(l1->memo_mu);
         l1->memo_partner_uid = l2->uid;
         l1->memo_slot = slot;
