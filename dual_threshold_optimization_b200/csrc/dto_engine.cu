@@ -219,6 +219,18 @@ int pull_counters(dto_b200_ctx *ctx) {
 
 }  // namespace
 
+namespace dto {
+void trim_batch_buffers(dto_b200_ctx *ctx, size_t keep_bytes) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_pb, &ctx->d_records, &ctx->d_status, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_words,
+                      &ctx->d_tstats, &ctx->d_minp};
+    for (DevBuf *b : bufs)
+        if (b->cap > keep_bytes) b->release();
+}
+}  // namespace dto
+
 extern "C" {
 
 const char *dto_b200_last_error(void) { return g_last_error.c_str(); }

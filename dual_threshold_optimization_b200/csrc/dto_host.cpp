@@ -47,6 +47,38 @@ namespace {
 
 std::atomic<uint64_t> g_next_list_uid{1};
 
+// Process-wide pool of idle engine contexts, per device: run_single_node / run_pairs take their contexts from here, so
+// only the first call on a device pays for stream, event and buffer creation (~25 ms per context) and repeated calls
+// reuse warm buffers.  Contexts are never shared between threads while in use; idle ones are kept until process exit.
+std::mutex g_pool_mu;
+std::vector<dto_b200_ctx *> g_pool[64];
+constexpr size_t kPoolPerDevice = 8;
+
+int pool_acquire(dto_b200_ctx **ctx_out, int device) {
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (device >= 0 && device < 64 && !g_pool[device].empty()) {
+            *ctx_out = g_pool[device].back();
+            g_pool[device].pop_back();
+            return DTO_B200_OK;
+        }
+    }
+    return dto_b200_create(ctx_out, device);
+}
+
+void pool_release(dto_b200_ctx *ctx, int device, bool healthy) {
+    if (!ctx) return;
+    if (healthy && device >= 0 && device < 64) {
+        dto::trim_batch_buffers(ctx, (size_t)256 << 20);
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        if (g_pool[device].size() < kPoolPerDevice) {
+            g_pool[device].push_back(ctx);
+            return;
+        }
+    }
+    dto_b200_destroy(ctx);
+}
+
 inline uint64_t hash_id(const std::string &s) {  // FNV-1a, finalised so that the low bits are well mixed
     uint64_t h = 1469598103934665603ull;
     for (unsigned char c : s) h = (h ^ c) * 1099511628211ull;
@@ -391,7 +423,7 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
         const bool has_work = !shard[g].empty() || (g == 0 && !unperm.empty());
         if (!has_work) return;
         dto_b200_ctx *ctx = nullptr;
-        int rc = dto_b200_create(&ctx, devs[g]);
+        int rc = pool_acquire(&ctx, devs[g]);
         if (rc == DTO_B200_OK) rc = dto_b200_load_lists(ctx, l1, l2, population);
         if (rc == DTO_B200_OK && g == 0 && !unperm.empty()) {
             dto_b200_record r;
@@ -404,7 +436,7 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
                                               records_out + shard[g][x].first, nullptr);
         if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
         rcs[g] = rc;
-        dto_b200_destroy(ctx);
+        pool_release(ctx, devs[g], rc == DTO_B200_OK);
     };
     if (G == 1) {
         worker(0);
@@ -445,7 +477,7 @@ int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200
         const size_t lo = std::min(g * per, n_pairs), hi = std::min(lo + per, n_pairs);
         if (lo >= hi) return;
         dto_b200_ctx *ctx = nullptr;
-        int rc = dto_b200_create(&ctx, devs[g]);
+        int rc = pool_acquire(&ctx, devs[g]);
         std::vector<dto_b200_record> recs(permutations + 1);
         for (size_t q = lo; rc == DTO_B200_OK && q < hi; ++q) {
             if (!lists1[q] || !lists2[q]) {
@@ -460,7 +492,7 @@ int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200
         }
         if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
         rcs[g] = rc;
-        dto_b200_destroy(ctx);
+        pool_release(ctx, devs[g], rc == DTO_B200_OK);
     };
     if (G == 1) {
         worker(0);
