@@ -90,6 +90,20 @@ def test_compute_population_size_rules():
     ids1, r1, ids2, r2, bg = H.load_test_data()
     a, b = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
     assert dto.compute_population_size(a, b, dto.FeatureList(bg)) == 30 == dto.compute_population_size(a, b, None)
+    # the id join runs on the per-list hash index: repeated ids of list 1 each count (FeatureList::intersect keeps every
+    # list-1 item whose id occurs in list 2, feature_list.rs:278-286), ids are compared as whole strings, and the index
+    # of a 20 000-feature list agrees with a plain Python set
+    dup1 = dto.RankedFeatureList.from_(["a", "a", "b"], [1, 2, 3])
+    assert dto.compute_population_size(dup1, dto.RankedFeatureList.from_(["a", "b", "c"], [1, 2, 3]), None) == 3
+    # ... which is why the reference accepts this pair too: 3 list-1 items found, both lists 3 long ("ab" is never looked up)
+    assert dto.compute_population_size(dup1, dto.RankedFeatureList.from_(["a", "b", "ab"], [1, 2, 3]), None) == 3
+    with pytest.raises(dto.DtoPanic, match="identical genes"):
+        dto.compute_population_size(dto.RankedFeatureList.from_(["a", "ab", "b"], [1, 2, 3]), dto.RankedFeatureList.from_(["a", "b", "c"], [1, 2, 3]), None)
+    big1, rb1, big2, rb2 = H.synthetic_pair(20000, 5, None)
+    x, y = dto.RankedFeatureList.from_(big1, rb1), dto.RankedFeatureList.from_(big2[:-1] + ["not-there"], rb2)
+    with pytest.raises(dto.DtoPanic, match="identical genes"):
+        dto.compute_population_size(x, y, None)
+    assert dto.compute_population_size(x, dto.RankedFeatureList.from_(big2, rb2), None) == 20000 == len(set(big1) & set(big2))
 
 
 def test_fdr_and_empirical_goldens():
