@@ -24,7 +24,8 @@ ERR_UNSUPPORTED = -5
 ERR_IO = -6
 
 FLAG_PERMUTED = 0x1
-FLAG_NEAR_TIE = 0x2
+FLAG_TIE_RESOLVED = 0x2  # the host libm settled a tie set the device could not (include/dto_b200.h)
+FLAG_HOST_PVALUE = 0x4
 FLAG_PATH_FULL = 0x8
 
 
@@ -83,6 +84,8 @@ class Stats(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("lptab_entries", C.c_uint64),
         ("table_cache_hits", C.c_uint64),
+        ("tasks_tie_resolved", C.c_uint64),
+        ("tie_cells_host", C.c_uint64),
     ]
 
 

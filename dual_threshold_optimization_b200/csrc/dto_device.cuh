@@ -27,8 +27,10 @@ constexpr double kEps = 1e-6;
 // lies below kZeroLo has p == 0.0 in the reference; between kZeroLo and kZeroHi it is evaluated exactly.
 // the ratio-recurrence tail reproduces log p of the reference to ~1e-10 (both sum the same ln-factorial table, whose
 // 7-term log pmf carries ~1e-10 absolute rounding); cells within kRefineEps of the minimum go to the exact stage
-constexpr double kRefineEps = 1e-8;
-constexpr uint32_t kRefinedBit = 0x80000000u;
+constexpr double kRefineEps = 1e-8;      // floor of Problem::refine_eps (which grows with ulp(lf[N]) for huge populations)
+constexpr uint32_t kRefinedBit = 0x80000000u;   // Cand::k flag: `v` is a log-p bound good to refine_eps
+constexpr uint32_t kEvalBit = 0x40000000u;      // Cand::k flag: `v` is the exact (statrs-order) p-value itself
+constexpr uint32_t kOverlapMask = 0x0000FFFFu;  // Cand::k: the overlap count
 constexpr double kZeroLo = -745.14;
 constexpr double kZeroHi = -745.12;
 
@@ -61,6 +63,33 @@ struct Problem {
     const uint16_t *bin2;      // [n2]
     const int32_t *slot2_of_1; // [n1]
     double level_log[kMaxLevels + 1];  // log tau_l ; [0] = +inf
+    // Error budget of everything derived from log pmf = a 7-term sum of ln-factorials: max(1e-8, 40 ulp(lf[N])).  At
+    // N = 20 000 (lf[N] ~ 1.8e5, ulp 2.9e-11) the floor applies; the accepted population limit 2^27 has ulp 4.8e-7.
+    double refine_eps;
+    double tab_slack;  // relative slack of the critical-overlap tables against the same rounding: max(1e-6, 4 refine_eps)
+};
+
+// One cell of a tie set the device could not settle (more than one distinct (K, n, k) inside the ambiguity window of the
+// minimum): re-evaluated on the host with the host libm, dto_engine.cu.
+struct TieEntry {
+    uint32_t task;
+    uint32_t ij;  // row << 16 | column
+    uint32_t k;
+};
+
+// What one scan launch reports besides the records (16 B, read back once per launch instead of a status word per task).
+struct ScanSummary {
+    uint32_t n_done;         // tasks that reached the end of finish_task
+    uint32_t n_full;         // tasks handed to the dense path (ids in full_list)
+    uint32_t n_tie_entries;  // TieEntry slots requested (> tie_cap: the overflowing tasks went to full_list instead)
+    uint32_t pad;
+};
+
+struct ScanOut {
+    ScanSummary *summary;
+    uint32_t *full_list;  // [n_tasks]
+    TieEntry *ties;       // [tie_cap]
+    uint32_t tie_cap;
 };
 
 // Row histogram of the scan kernel: lane = j / CH owns columns m = j % CH; columns (2q, 2q+1) of a lane share the

@@ -91,14 +91,19 @@ struct dto_b200_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool has_problem = false;
     Problem P{};
     // problem tables
     DevBuf d_c1, d_c2, d_thr1, d_thr2, d_lf, d_rowA, d_colB, d_kcrit, d_dslot2, d_bin1, d_bin2, d_slot2, d_meta, d_lptab, d_counts;
     // batch state
-    DevBuf d_pb, d_records, d_status, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv,
-        d_err, d_pair, d_minp, d_tstats, d_words;
+    DevBuf d_pb, d_records, d_counters, d_H, d_pv, d_logp, d_perm1, d_perm2, d_inv, d_err, d_pair, d_minp, d_tstats,
+        d_words;
+    // what a scan launch reports besides records: summary word block, ids of tasks for the dense path, unsettled tie sets
+    DevBuf d_summary, d_full_list, d_ties, d_patch_idx, d_patch_rec, d_best_cell, d_collect;
+    DevBuf d_slotmaps, d_seeds;  // batched list pairs: per-pair gene maps (unpermuted tasks) and per-pair Philox seeds
+    PinnedBuf h_summary, h_ties, h_patch;
+    std::vector<uint32_t> h_c1, h_c2, h_thr1, h_thr2;  // host copies of the current problem (tie resolution builds records)
     bool opt_task_stats = false;
     bool opt_swar = true;
     bool opt_table_cache = true;
@@ -112,7 +117,7 @@ struct dto_b200_ctx {
     uint32_t tab_never = 0;
     std::vector<uint32_t> tab_c1, tab_c2;
     int last_batch_n = 0;
-    PinnedBuf h_records, h_status, h_stage;
+    PinnedBuf h_records, h_stage;
     // options
     int opt_batch = 0;  // 0 = auto
     int opt_warps = kScanThreads / 32;
@@ -141,14 +146,113 @@ int auto_batch(const dto_b200_ctx *ctx) {
     return (int)b;
 }
 
-// Runs the scan over n tasks whose partner-slot rows are already in ctx->d_pb; results land in
-// ctx->d_records[0..n).  Degenerate tasks (minimum p >= 1: no cell beats the short-circuited ones) go to the dense path.
-int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags) {
+// The reference's own evaluation of one cell on this host (statrs order, host libm): see dto_host_math.hpp.
+double host_p(const dto_b200_ctx *ctx, uint32_t K, uint32_t n, uint32_t k) {
+    return host_hypergeom_pvalue_exact(ctx->lf_host.data(), ctx->P.N, K, n, k);
+}
+
+struct HostCell {
+    uint32_t ij, k;
+};
+
+// optimize_main.rs:73-116 over a handful of cells, with p re-evaluated on the host: smallest p (exact ==), then largest
+// overlap, then smallest (rank1, rank2) == smallest (row, column).  Cells with equal (K, n, k) are evaluated once.
+dto_b200_record resolve_on_host(dto_b200_ctx *ctx, const HostCell *cells, size_t n_cells, uint32_t flags) {
+    const int T2 = ctx->P.T2;
+    (void)T2;
+    double best_p = INFINITY;
+    uint32_t best_k = 0, best_ij = 0xFFFFFFFFu;
+    uint32_t lastK = ~0u, lastn = ~0u, lastk = ~0u;
+    double lastp = 0.0;
+    for (size_t x = 0; x < n_cells; ++x) {
+        const uint32_t i = cells[x].ij >> 16, j = cells[x].ij & 0xFFFFu, k = cells[x].k;
+        const uint32_t K = ctx->h_c1[i], n = ctx->h_c2[j];
+        double p;
+        if (K == lastK && n == lastn && k == lastk) {
+            p = lastp;
+        } else {
+            p = host_p(ctx, K, n, k);
+            lastK = K, lastn = n, lastk = k, lastp = p;
+        }
+        const bool better = best_ij == 0xFFFFFFFFu || p < best_p || (p == best_p && (k > best_k || (k == best_k && cells[x].ij < best_ij)));
+        if (better) best_p = p, best_k = k, best_ij = cells[x].ij;
+    }
+    ctx->stats.tie_cells_host += n_cells;
+    const uint32_t bi = best_ij >> 16, bj = best_ij & 0xFFFFu;
+    dto_b200_record r;
+    r.rank1 = ctx->h_thr1[bi];
+    r.rank2 = ctx->h_thr2[bj];
+    r.set1_len = ctx->h_c1[bi];
+    r.set2_len = ctx->h_c2[bj];
+    r.intersection_size = best_k;
+    r.flags = flags | DTO_B200_FLAG_HOST_PVALUE;
+    r.population_size = ctx->P.N;
+    r.pvalue = best_p;
+    return r;
+}
+
+// Dense path for ONE task whose partner-slot row is pbrow: every cell evaluated on the device in statrs order, device
+// argmin, then the cells inside the ambiguity window of that minimum go to the host, which settles the optimum exactly
+// as the reference would (host libm).  The record (host-evaluated p) is returned and, if d_dst != nullptr, also stored there.
+int dense_task(dto_b200_ctx *ctx, const uint16_t *pbrow, uint32_t flags, dto_b200_record *d_dst, dto_b200_record *h_out) {
+    const Problem &P = ctx->P;
+    const size_t cells = (size_t)P.T1 * P.T2;
+    CUDA_TRY(ctx->d_H.ensure(cells * 4));
+    CUDA_TRY(ctx->d_pv.ensure(cells * 8));
+    CUDA_TRY(ctx->d_best_cell.ensure(16 + sizeof(dto_b200_record)));
+    CUDA_TRY(ctx->d_collect.ensure(cells * sizeof(uint2)));
+    uint32_t *d_bc = ctx->d_best_cell.as<uint32_t>();  // [0] argmin cell, [1] collect count, then a scratch record
+    dto_b200_record *d_rec = reinterpret_cast<dto_b200_record *>(d_bc + 4);
+    CUDA_TRY(launch_full_grid(P, pbrow, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), nullptr, ctx->stream));
+    CUDA_TRY(launch_full_argmin(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), flags, d_rec, d_bc, ctx->stream));
+    CUDA_TRY(launch_full_collect(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), d_bc, d_bc + 1, ctx->d_collect.as<uint2>(), ctx->stream));
+    ctx->stats.kernel_launches += 6;
+    ctx->stats.tasks_full += 1;
+    uint32_t head[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(head, d_bc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const uint32_t cnt = head[1];
+    if (cnt == 0 || cnt > cells) return fail(DTO_B200_ERR_CUDA, "dense path returned an invalid tie count (%u)", cnt);
+    std::vector<uint2> got(cnt);
+    CUDA_TRY(cudaMemcpy(got.data(), ctx->d_collect.p, (size_t)cnt * sizeof(uint2), cudaMemcpyDeviceToHost));
+    ctx->stats.d2h_bytes += 8 + (uint64_t)cnt * sizeof(uint2);
+    std::vector<HostCell> hc(cnt);
+    for (uint32_t x = 0; x < cnt; ++x) {
+        hc[x].ij = ((got[x].x / (uint32_t)P.T2) << 16) | (got[x].x % (uint32_t)P.T2);
+        hc[x].k = got[x].y;
+    }
+    // atomics fill the list in arbitrary order; equal (K, n, k) runs are evaluated once when adjacent
+    std::sort(hc.begin(), hc.end(), [&](const HostCell &a, const HostCell &b) {
+        const uint32_t Ka = ctx->h_c1[a.ij >> 16], Kb = ctx->h_c1[b.ij >> 16];
+        if (Ka != Kb) return Ka < Kb;
+        const uint32_t na = ctx->h_c2[a.ij & 0xFFFFu], nb = ctx->h_c2[b.ij & 0xFFFFu];
+        if (na != nb) return na < nb;
+        if (a.k != b.k) return a.k < b.k;
+        return a.ij < b.ij;
+    });
+    dto_b200_record r = resolve_on_host(ctx, hc.data(), hc.size(), flags | DTO_B200_FLAG_PATH_FULL | (cnt > 1 ? DTO_B200_FLAG_TIE_RESOLVED : 0u));
+    if (cnt > 1) ctx->stats.tasks_tie_resolved += 1;
+    if (d_dst) {
+        CUDA_TRY(cudaMemcpy(d_dst, &r, sizeof(r), cudaMemcpyHostToDevice));
+        ctx->stats.h2d_bytes += sizeof(r);
+    }
+    if (h_out) *h_out = r;
+    return DTO_B200_OK;
+}
+
+// Runs the scan over n tasks whose partner-slot rows are already in ctx->d_pb; results land in ctx->d_records[0..n).
+// Tasks whose tie set needs the host libm (optimize_main.rs:73-80 compares p with ==) are settled here and patched
+// into d_records; degenerate tasks (minimum p >= 1, tie set larger than the buffer) go through the dense path.
+// flags_unperm_first: the first `n_unperm_first` tasks carry no PERMUTED flag (batched list pairs).
+int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags, int n_plain = 0) {
     const Problem &P = ctx->P;
     CUDA_TRY(ctx->d_records.ensure((size_t)n * sizeof(dto_b200_record)));
-    CUDA_TRY(ctx->d_status.ensure((size_t)n * 4));
-    CUDA_TRY(ctx->h_status.ensure((size_t)n * 4));
-    CUDA_TRY(cudaMemsetAsync(ctx->d_status.p, 0xFF, (size_t)n * 4, ctx->stream));
+    const uint32_t tie_cap = (uint32_t)std::max<size_t>(4096, (size_t)n / 2);
+    CUDA_TRY(ctx->d_summary.ensure(sizeof(ScanSummary)));
+    CUDA_TRY(ctx->h_summary.ensure(sizeof(ScanSummary)));
+    CUDA_TRY(ctx->d_full_list.ensure((size_t)n * 4));
+    CUDA_TRY(ctx->d_ties.ensure((size_t)tie_cap * sizeof(TieEntry)));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_summary.p, 0, sizeof(ScanSummary), ctx->stream));
     int warps = ctx->opt_warps;
     const int ctas_per_sm = (P.CH > 32) ? 1 : kScanCtasPerSm;
     while (warps > 1 && scan_smem_bytes(P.CH, P.T1, warps) + 1024 > (size_t)(228 * 1024) / ctas_per_sm) --warps;
@@ -161,42 +265,87 @@ int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags) {
         CUDA_TRY(cudaMemsetAsync(ctx->d_tstats.p, 0, (size_t)n * 4 * kTaskStatWords, ctx->stream));
     }
     ctx->last_batch_n = n;
+    ScanOut so;
+    so.summary = ctx->d_summary.as<ScanSummary>();
+    so.full_list = ctx->d_full_list.as<uint32_t>();
+    so.ties = ctx->d_ties.as<TieEntry>();
+    so.tie_cap = tie_cap;
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters.as<unsigned long long>() + 7, 0, 8, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev[0], ctx->stream));
-    CUDA_TRY(launch_scan(P, ctx->d_pb.as<uint16_t>(), n, flags, ctx->d_records.as<dto_b200_record>(),
-                         ctx->d_status.as<uint32_t>(), ctx->d_counters.as<unsigned long long>(),
+    CUDA_TRY(launch_scan(P, ctx->d_pb.as<uint16_t>(), n, n_plain, flags, ctx->d_records.as<dto_b200_record>(), so,
+                         ctx->d_counters.as<unsigned long long>(),
                          ctx->opt_task_stats ? ctx->d_tstats.as<uint32_t>() : nullptr, grid, warps, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
     ctx->stats.kernel_launches += 1;
     ctx->stats.last_scan_launches += 1;
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += (uint64_t)n * 4;
+    ScanSummary *sum = ctx->h_summary.as<ScanSummary>();
+    CUDA_TRY(cudaMemcpyAsync(sum, ctx->d_summary.p, sizeof(ScanSummary), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += sizeof(ScanSummary);
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->stats.last_scan_kernel_ms += ms;
+    if (sum->n_done != (uint32_t)n)
+        return fail(DTO_B200_ERR_CUDA, "scan kernel finished %u of %d tasks", sum->n_done, n);
+    const uint32_t n_full = sum->n_full;
+    const uint32_t n_ties = std::min(sum->n_tie_entries, tie_cap);  // reservations past the cap were redirected to full_list
+    ctx->stats.tasks_fast += (uint64_t)(n - (int)n_full);
 
-    const uint32_t *st = ctx->h_status.as<uint32_t>();
-    std::vector<uint32_t> full;
-    for (int t = 0; t < n; ++t) {
-        if (st[t] == 0) continue;
-        if (st[t] == 2) full.push_back((uint32_t)t);
-        else return fail(DTO_B200_ERR_CUDA, "scan kernel left task %d unprocessed (status %u)", t, st[t]);
-    }
-    ctx->stats.tasks_fast += (uint64_t)(n - (int)full.size());
-    if (!full.empty()) {
-        const size_t cells = (size_t)P.T1 * P.T2;
-        CUDA_TRY(ctx->d_H.ensure(cells * 4));
-        CUDA_TRY(ctx->d_pv.ensure(cells * 8));
-        for (uint32_t t : full) {
-            CUDA_TRY(launch_full_grid(P, ctx->d_pb.as<uint16_t>() + (size_t)t * P.pb_stride, ctx->d_H.as<uint32_t>(),
-                                      ctx->d_pv.as<double>(), nullptr, ctx->stream));
-            CUDA_TRY(launch_full_argmin(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), flags,
-                                        ctx->d_records.as<dto_b200_record>() + t, ctx->stream));
-            ctx->stats.kernel_launches += 5;
-            ctx->stats.tasks_full += 1;
-        }
+    if (n_ties) {
+        // entries of one task were reserved as one block, so they are contiguous
+        CUDA_TRY(ctx->h_ties.ensure((size_t)n_ties * sizeof(TieEntry)));
+        TieEntry *te = ctx->h_ties.as<TieEntry>();
+        CUDA_TRY(cudaMemcpyAsync(te, ctx->d_ties.p, (size_t)n_ties * sizeof(TieEntry), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += (uint64_t)n_ties * sizeof(TieEntry);
+        std::vector<uint32_t> idx;
+        std::vector<dto_b200_record> rec;
+        std::vector<HostCell> hc;
+        for (uint32_t x = 0; x < n_ties;) {
+            uint32_t y = x;
+            hc.clear();
+            if (te[x].task == 0xFFFFFFFFu) {  // void part of a reservation that straddled the end of the pool
+                ++x;
+                continue;
+            }
+            while (y < n_ties && te[y].task == te[x].task) {
+                hc.push_back({te[y].ij, te[y].k});
+                ++y;
+            }
+            if (te[x].task >= (uint32_t)n) return fail(DTO_B200_ERR_CUDA, "tie pool entry %u names task %u of %d", x, te[x].task, n);
+            const uint32_t tf = (int)te[x].task < n_plain ? (flags & ~DTO_B200_FLAG_PERMUTED) : flags;
+            idx.push_back(te[x].task);
+            rec.push_back(resolve_on_host(ctx, hc.data(), hc.size(), tf | DTO_B200_FLAG_TIE_RESOLVED));
+            x = y;
+        }
+        ctx->stats.tasks_tie_resolved += idx.size();
+        const size_t m = idx.size();
+        CUDA_TRY(ctx->h_patch.ensure(m * (sizeof(dto_b200_record) + 4)));
+        CUDA_TRY(ctx->d_patch_idx.ensure(m * 4));
+        CUDA_TRY(ctx->d_patch_rec.ensure(m * sizeof(dto_b200_record)));
+        dto_b200_record *hp = ctx->h_patch.as<dto_b200_record>();
+        uint32_t *hi = reinterpret_cast<uint32_t *>(hp + m);
+        memcpy(hp, rec.data(), m * sizeof(dto_b200_record));
+        memcpy(hi, idx.data(), m * 4);
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_patch_rec.p, hp, m * sizeof(dto_b200_record), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_patch_idx.p, hi, m * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += m * (sizeof(dto_b200_record) + 4);
+        CUDA_TRY(launch_patch_records(ctx->d_patch_idx.as<uint32_t>(), ctx->d_patch_rec.as<dto_b200_record>(), (int)m,
+                                      ctx->d_records.as<dto_b200_record>(), ctx->stream));
+        ctx->stats.kernel_launches += 1;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the pinned staging buffers are reused by the next launch
+    }
+    if (n_full) {
+        std::vector<uint32_t> full(n_full);
+        CUDA_TRY(cudaMemcpy(full.data(), ctx->d_full_list.p, (size_t)n_full * 4, cudaMemcpyDeviceToHost));
+        ctx->stats.d2h_bytes += (uint64_t)n_full * 4;
+        for (uint32_t t : full) {
+            if (t >= (uint32_t)n) return fail(DTO_B200_ERR_CUDA, "dense-path list names task %u of %d", t, n);
+            int rc = dense_task(ctx, ctx->d_pb.as<uint16_t>() + (size_t)t * P.pb_stride,
+                                (int)t < n_plain ? (flags & ~DTO_B200_FLAG_PERMUTED) : flags,
+                                ctx->d_records.as<dto_b200_record>() + t, nullptr);
+            if (rc) return rc;
+        }
     }
     return DTO_B200_OK;
 }
@@ -224,8 +373,8 @@ void trim_batch_buffers(dto_b200_ctx *ctx, size_t keep_bytes) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->d_pb, &ctx->d_records, &ctx->d_status, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_words,
-                      &ctx->d_tstats, &ctx->d_minp};
+    DevBuf *bufs[] = {&ctx->d_pb, &ctx->d_records, &ctx->d_full_list, &ctx->d_ties, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv,
+                      &ctx->d_words, &ctx->d_tstats, &ctx->d_minp, &ctx->d_slotmaps, &ctx->d_seeds};
     for (DevBuf *b : bufs)
         if (b->cap > keep_bytes) b->release();
 }
@@ -287,13 +436,16 @@ void dto_b200_destroy(dto_b200_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf *bufs[] = {&ctx->d_c1, &ctx->d_c2, &ctx->d_thr1, &ctx->d_thr2, &ctx->d_lf, &ctx->d_rowA, &ctx->d_colB,
                       &ctx->d_kcrit, &ctx->d_meta, &ctx->d_lptab, &ctx->d_counts, &ctx->d_dslot2, &ctx->d_bin1, &ctx->d_bin2, &ctx->d_slot2, &ctx->d_pb,
-                      &ctx->d_records, &ctx->d_status, &ctx->d_counters, &ctx->d_H,
+                      &ctx->d_records, &ctx->d_counters, &ctx->d_H,
                       &ctx->d_pv, &ctx->d_logp, &ctx->d_perm1, &ctx->d_perm2, &ctx->d_inv, &ctx->d_err, &ctx->d_pair,
-                      &ctx->d_minp, &ctx->d_tstats, &ctx->d_words};
+                      &ctx->d_minp, &ctx->d_tstats, &ctx->d_words, &ctx->d_summary, &ctx->d_full_list, &ctx->d_ties,
+                      &ctx->d_patch_idx, &ctx->d_patch_rec, &ctx->d_best_cell, &ctx->d_collect, &ctx->d_slotmaps, &ctx->d_seeds};
     for (DevBuf *b : bufs) b->release();
     ctx->h_records.release();
-    ctx->h_status.release();
     ctx->h_stage.release();
+    ctx->h_summary.release();
+    ctx->h_ties.release();
+    ctx->h_patch.release();
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -317,7 +469,8 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
     } else if (s == "task_stats") {
         ctx->opt_task_stats = value != 0;
     } else if (s == "levels") {
-        if (value < 0 || value > kMaxLevels) return fail(DTO_B200_ERR_INVALID, "levels must be 0..%d", kMaxLevels);
+        // fewer than two levels leave no tabulated range (tau_1 .. tau_levels), and level 0 alone certifies nothing
+        if (value < 2 || value > kMaxLevels) return fail(DTO_B200_ERR_INVALID, "levels must be 2..%d", kMaxLevels);
         if (ctx->has_problem) return fail(DTO_B200_ERR_STATE, "set 'levels' before dto_b200_set_problem");
         ctx->opt_levels = (int)value;
     } else {
@@ -453,6 +606,13 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     std::vector<double> rowA(T1), colB(T2);
     for (size_t i = 0; i < T1; ++i) rowA[i] = lf[c1[i]] + lf[population - c1[i]];
     for (size_t j = 0; j < T2; ++j) colB[j] = lf[c2[j]] + lf[population - c2[j]] - lf[population];
+    {
+        // error budget of log pmf (a 7-term sum of ln-factorials of magnitude <= lf[N]): see Problem::refine_eps
+        const double top = lf[population] > 1.0 ? lf[population] : 1.0;
+        const double ulp = std::nextafter(top, INFINITY) - top;
+        P.refine_eps = std::max(kRefineEps, 40.0 * ulp);
+        P.tab_slack = std::max(1e-6, 4.0 * P.refine_eps);
+    }
     P.level_log[0] = INFINITY;
     // tau_1 = 0.95 ends the unscreened phase at once; then half-octave steps 0.5, 0.354, 0.25, ... so that a permutation
     // whose running minimum sits just above a level still screens out everything more than ~1.4x above it
@@ -465,6 +625,10 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
         ctx->stats.h2d_bytes += bytes;
         return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
+    ctx->h_c1 = c1;
+    ctx->h_c2 = c2;
+    ctx->h_thr1.assign(thr1, thr1 + T1);
+    ctx->h_thr2.assign(thr2, thr2 + T2);
     const bool tables_cached = ctx->opt_table_cache && ctx->tab_valid && ctx->tab_N == population &&
                                ctx->tab_levels == P.levels && ctx->tab_never == P.never && ctx->tab_c1 == c1 &&
                                ctx->tab_c2 == c2;
@@ -551,7 +715,7 @@ int dto_b200_run_unpermuted(dto_b200_ctx *ctx, dto_b200_record *record_out) {
     if (!record_out) return fail(DTO_B200_ERR_INVALID, "null record_out");
     const Problem &P = ctx->P;
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
-    CUDA_TRY(launch_compose(P, nullptr, nullptr, 1, nullptr, ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
+    CUDA_TRY(launch_compose(P, nullptr, nullptr, nullptr, 1, nullptr, ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
     ctx->stats.kernel_launches += 1;
     ctx->stats.last_scan_kernel_ms = 0;
     ctx->stats.last_sigma_kernel_ms = 0;
@@ -559,18 +723,8 @@ int dto_b200_run_unpermuted(dto_b200_ctx *ctx, dto_b200_record *record_out) {
     // One task cannot fill the GPU through the warp-per-permutation scan, and for strongly concordant lists nearly
     // every cell is deep in the tail; the dense grid (every cell evaluated in statrs order on all SMs) is both exact
     // and fast here: optimize(l1, l2, permute = false, ..) == argmin of the debug grid (optimize_main.rs:73-116).
-    const size_t cells = (size_t)P.T1 * P.T2;
-    CUDA_TRY(ctx->d_H.ensure(cells * 4));
-    CUDA_TRY(ctx->d_pv.ensure(cells * 8));
-    CUDA_TRY(ctx->d_records.ensure(sizeof(dto_b200_record)));
-    CUDA_TRY(launch_full_grid(P, ctx->d_pb.as<uint16_t>(), ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), nullptr, ctx->stream));
-    CUDA_TRY(launch_full_argmin(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), 0u, ctx->d_records.as<dto_b200_record>(), ctx->stream));
-    ctx->stats.kernel_launches += 5;
-    ctx->stats.tasks_full += 1;
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(cudaMemcpy(record_out, ctx->d_records.p, sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
-    ctx->stats.d2h_bytes += sizeof(dto_b200_record);
-    return DTO_B200_OK;
+    // The optimum itself is settled on the host (host libm), so the record's p is bit-identical to the reference's.
+    return dense_task(ctx, ctx->d_pb.as<uint16_t>(), 0u, nullptr, record_out);
 }
 
 int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t *perm2, size_t Pn,
@@ -597,7 +751,7 @@ int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, cons
         CUDA_TRY(cudaMemcpyAsync(ctx->d_perm2.p, perm2 + done * P.n2, (size_t)n * P.n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
         ctx->stats.h2d_bytes += (uint64_t)n * ((uint64_t)P.n1 + P.n2) * 4;
         CUDA_TRY(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
-        CUDA_TRY(launch_compose(P, ctx->d_perm1.as<uint32_t>(), ctx->d_perm2.as<uint32_t>(), n, ctx->d_inv.as<uint32_t>(),
+        CUDA_TRY(launch_compose(P, ctx->d_perm1.as<uint32_t>(), ctx->d_perm2.as<uint32_t>(), nullptr, n, ctx->d_inv.as<uint32_t>(),
                                 ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
         ctx->stats.kernel_launches += 5;
         int err = 0;
@@ -633,17 +787,8 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
     ctx->stats.last_sigma_kernel_ms = 0;
     ctx->stats.last_scan_launches = 0;
     if (h_records || h_minp) CUDA_TRY(ctx->h_records.ensure(std::min(batch, Pn) * sizeof(dto_b200_record)));
-    cudaEvent_t run_begin = nullptr, run_end = nullptr;
-    CUDA_TRY(cudaEventCreate(&run_begin));
-    CUDA_TRY(cudaEventCreate(&run_end));
+    cudaEvent_t run_begin = ctx->ev[4], run_end = ctx->ev[5];
     CUDA_TRY(cudaEventRecord(run_begin, ctx->stream));
-    struct EvGuard {
-        cudaEvent_t a, b;
-        ~EvGuard() {
-            cudaEventDestroy(a);
-            cudaEventDestroy(b);
-        }
-    } guard{run_begin, run_end};
     for (size_t done = 0; done < Pn; done += batch) {
         const int n = (int)std::min(batch, Pn - done);
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
@@ -734,7 +879,7 @@ int dto_b200_grid_debug(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t
         CUDA_TRY(cudaMemcpyAsync(ctx->d_perm2.p, perm2, (size_t)P.n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     CUDA_TRY(launch_compose(P, perm1 ? ctx->d_perm1.as<uint32_t>() : nullptr, perm2 ? ctx->d_perm2.as<uint32_t>() : nullptr,
-                            1, ctx->d_inv.as<uint32_t>(), ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
+                            nullptr, 1, ctx->d_inv.as<uint32_t>(), ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
     int err = 0;
     CUDA_TRY(cudaMemcpyAsync(&err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -756,7 +901,14 @@ int dto_b200_hypergeometric_pvalues(dto_b200_ctx *ctx, const uint64_t *N, const 
     if (count == 0) return DTO_B200_OK;
     if (!N || !K || !n || !k || !pvalue_out) return fail(DTO_B200_ERR_INVALID, "null argument");
     uint64_t maxN = 0;
-    for (size_t x = 0; x < count; ++x) maxN = std::max(maxN, N[x]);
+    for (size_t x = 0; x < count; ++x) {
+        maxN = std::max(maxN, N[x]);
+        // Hypergeometric::new(N, K, n).expect(..) (hypergeometric_pvalue.rs:40-41) panics unless K <= N and n <= N
+        if (K[x] > N[x] || n[x] > N[x])
+            return fail(DTO_B200_ERR_PANIC,
+                        "Failed to create hypergeometric distribution: quadruple %zu has successes %llu / draws %llu > population %llu",
+                        x, (unsigned long long)K[x], (unsigned long long)n[x], (unsigned long long)N[x]);
+    }
     if (maxN > ((uint64_t)1 << 27)) return fail(DTO_B200_ERR_UNSUPPORTED, "population exceeds 2^27");
     std::vector<double> lf;
     host_fill_ln_factorial(lf, maxN);

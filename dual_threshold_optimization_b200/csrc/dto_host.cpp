@@ -10,6 +10,7 @@
 #include <cstring>
 #include <atomic>
 #include <fstream>
+#include <memory>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -18,6 +19,7 @@
 #include <unordered_set>
 #include <vector>
 
+#include "dto_host_math.hpp"
 #include "dto_internal.hpp"
 
 using dto::fail;
@@ -125,6 +127,25 @@ inline int32_t find_id(const dto_b200_ranked_list *l, const std::string &id, uin
         x = (x + 1) & (cap - 1);
     }
     return -1;
+}
+
+// ln_factorial tables for the host-side re-evaluations of the epilogue, kept per population (building one costs ~1 ms
+// per 20 000 entries); a handful of populations at most are alive in one process (one per list pair shape)
+std::mutex g_lf_mu;
+std::vector<std::pair<uint64_t, std::shared_ptr<std::vector<double>>>> g_lf_cache;
+
+std::shared_ptr<std::vector<double>> host_lf_table(uint64_t N) {
+    {
+        std::lock_guard<std::mutex> lock(g_lf_mu);
+        for (auto &e : g_lf_cache)
+            if (e.first == N) return e.second;
+    }
+    auto t = std::make_shared<std::vector<double>>();
+    dto::host_fill_ln_factorial(*t, N);
+    std::lock_guard<std::mutex> lock(g_lf_mu);
+    if (g_lf_cache.size() >= 4) g_lf_cache.erase(g_lf_cache.begin());
+    g_lf_cache.emplace_back(N, t);
+    return t;
 }
 
 std::string trim_ws(const std::string &s) {
@@ -487,7 +508,7 @@ int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200
             rc = dto_b200_load_lists(ctx, lists1[q], lists2[q], populations[q]);
             if (rc == DTO_B200_OK) rc = dto_b200_run_unpermuted(ctx, &recs[0]);
             if (rc == DTO_B200_OK && permutations)
-                rc = dto_b200_run_permuted_philox(ctx, seed + (uint64_t)q * 0x9E3779B97F4A7C15ull, 0, permutations, recs.data() + 1, nullptr);
+                rc = dto_b200_run_permuted_philox(ctx, seed + (uint64_t)q * 0x9E3779B97F4A7C15ull, 1, permutations, recs.data() + 1, nullptr);
             if (rc == DTO_B200_OK) rc = dto_b200_empirical_pvalue(recs.data(), recs.size(), &results_out[q]);
         }
         if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
@@ -551,9 +572,35 @@ int dto_b200_empirical_pvalue(const dto_b200_record *records, size_t n, dto_b200
         out->empirical_pvalue = 1.0;
         return DTO_B200_OK;
     }
+    // count of permuted p <= unpermuted p (:160-165).  The reference compares values of ONE evaluator (its libm); here
+    // permuted records usually carry device-evaluated p-values.  Wherever the two sides are closer than the ambiguity
+    // window (e.g. a permutation reproducing the unpermuted (K, n, k), or its mirror image (n, K, k)), both are
+    // re-evaluated on the host in statrs order, so the comparison is the one the reference makes on this machine.
     size_t c = 0;
-    for (size_t i = 0; i < n; ++i)
-        if ((records[i].flags & DTO_B200_FLAG_PERMUTED) && records[i].pvalue <= unperm->pvalue) ++c;
+    const double pu = unperm->pvalue;
+    std::shared_ptr<std::vector<double>> lf;
+    double pu_host = 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        const dto_b200_record &r = records[i];
+        if (!(r.flags & DTO_B200_FLAG_PERMUTED)) continue;
+        if (!dto::host_pvalues_ambiguous(r.pvalue, pu) || r.population_size != unperm->population_size ||
+            r.set1_len > r.population_size || r.set2_len > r.population_size) {
+            if (r.pvalue <= pu) ++c;
+            continue;
+        }
+        if (!lf) {
+            if (unperm->population_size > ((uint64_t)1 << 27) || unperm->set1_len > unperm->population_size ||
+                unperm->set2_len > unperm->population_size) {  // not a record this library produced: compare as given
+                if (r.pvalue <= pu) ++c;
+                continue;
+            }
+            lf = host_lf_table(unperm->population_size);
+            pu_host = dto::host_hypergeom_pvalue_exact(lf->data(), unperm->population_size, unperm->set1_len, unperm->set2_len,
+                                                       unperm->intersection_size);
+        }
+        const double pr = dto::host_hypergeom_pvalue_exact(lf->data(), r.population_size, r.set1_len, r.set2_len, r.intersection_size);
+        if (pr <= pu_host) ++c;
+    }
     out->empirical_pvalue = (double)c / (double)n_perm;  // no +1 correction (:160-165)
     return DTO_B200_OK;
 }

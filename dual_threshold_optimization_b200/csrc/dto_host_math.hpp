@@ -45,4 +45,43 @@ inline void host_fill_ln_factorial(std::vector<double> &lf, uint64_t N) {
     }
 }
 
+// hypergeometric_pvalue(N, K, n, k) exactly as the reference evaluates it on THIS host (hypergeometric_pvalue.rs:33-50 ->
+// statrs 0.17.1 Hypergeometric::sf): ascending direct sum of exp(lnC(K,i) + lnC(N-K,n-i) - lnC(N,n)) with the host libm's
+// exp() -- the function Rust's f64::exp links to.  Same early exit as the device version (bit-preserving: past the mode a
+// term below 2^-55 of the accumulator cannot change it, nor can any later one).  `lf` = host_fill_ln_factorial(N).
+// Used wherever the reference's comparison of two p-values (== / < in optimize_main.rs:73-80, <= in
+// empirical_pvalue.rs:160-165) could hinge on the last ulp of exp(): the device shortlists, the host decides.
+inline double host_hypergeom_pvalue_exact(const double *lf, uint64_t N, uint64_t K, uint64_t n, uint64_t k) {
+    if (K > N || n > N) return NAN;
+    if (k == 0) return 1.0;
+    const uint64_t x = k - 1;
+    const uint64_t mn = (n + K > N) ? (n + K - N) : 0;
+    const uint64_t mx = K < n ? K : n;
+    if (x < mn) return 1.0;
+    if (x >= mx) return 0.0;
+    const double ln_denom = (lf[N] - lf[n]) - lf[N - n];
+    const uint64_t mode = (uint64_t)(((double)(n + 1) * (double)(K + 1)) / (double)(N + 2));
+    const double lfK = lf[K], lfNK = lf[N - K];
+    const uint64_t NK = N - K;
+    double acc = 0.0;
+    for (uint64_t i = x + 1; i <= mx; ++i) {
+        const double a = (lfK - lf[i]) - lf[K - i];
+        const uint64_t ni = n - i;
+        const double b = (ni > NK) ? -INFINITY : (lfNK - lf[ni]) - lf[NK - ni];
+        const double term = std::exp((a + b) - ln_denom);
+        acc += term;
+        if (i > mode + 1 && term <= acc * 0x1p-55) break;
+    }
+    return acc;
+}
+
+// Two p-values closer than this are "ambiguous": the device's exp() (<= 1 ulp) and the host libm's may order them
+// differently (worst case ~1.4e-14 relative over a 60-term tail; the absolute part covers sums of subnormal terms).
+constexpr double kTieRel = 1e-12;
+constexpr double kTieAbs = 1e-320;
+inline bool host_pvalues_ambiguous(double a, double b) {
+    const double lo = a < b ? a : b, hi = a < b ? b : a;
+    return hi <= lo * (1.0 + kTieRel) + kTieAbs;
+}
+
 }  // namespace dto

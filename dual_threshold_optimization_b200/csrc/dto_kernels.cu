@@ -12,6 +12,7 @@
 //   K3  full_* kernels         dense T1 x T2 grid (debug=true analogue, optimize_main.rs:68-70) + exact argmin;
 //                              also the last-resort path for degenerate tasks (min p >= 1)
 #include "dto_kernels.cuh"
+#include "dto_host_math.hpp"  // kTieRel / kTieAbs: the ambiguity window shared with the host resolver
 
 #include <algorithm>
 
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
             if (k >= tab_lo && k < tab_lo + tab_n) lptab[meta[cell].x + (uint32_t)(k - tab_lo)] = log(S);
             if (k <= tab_lo) break;
         } else {
-            while (l >= 1 && S > exp(P.level_log[l]) * (1.0 + 1e-6)) {
+            while (l >= 1 && S > exp(P.level_log[l]) * (1.0 + P.tab_slack)) {
                 const uint16_t v = (k + 1 <= upper) ? (uint16_t)(k + 1) : (uint16_t)never;
                 dst[l * level_stride] = v;
                 if (l == P.levels) kcL = v;
@@ -552,19 +553,27 @@ __global__ void check_perm_kernel(const uint32_t *__restrict__ perm, uint32_t n,
     if (v >= n || inv[t * n + v] != (uint32_t)(idx - t * n)) atomicExch(err, 1);  // duplicate entry
 }
 
+// slot2_maps != nullptr: task t uses its own gene map slot2_maps[t * n1 ..] (batched list pairs that share one rank
+// structure but not their gene order); otherwise every task uses P.slot2_of_1.
 __global__ void compose_pairing_kernel(const Problem P, const uint32_t *__restrict__ perm1,
-                                       const uint32_t *__restrict__ inv2, int n_tasks, uint16_t *__restrict__ pb) {
+                                       const uint32_t *__restrict__ inv2, const int32_t *__restrict__ slot2_maps,
+                                       int n_tasks, uint16_t *__restrict__ pb) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)P.pb_stride * n_tasks) return;
     const size_t t = idx / P.pb_stride;
+    const int32_t *__restrict__ slot2_base = slot2_maps ? slot2_maps + t * P.n1 : P.slot2_of_1;
     const uint32_t j = (uint32_t)(idx - t * P.pb_stride);
     uint16_t v = kNoSlot;
     if (j < P.n1_eff) {
+        // perm1 / inv2 come from the caller: an invalid row (entry out of range, or a duplicate that left an inverse slot
+        // at its 0xFFFFFFFF fill) already raised *err in the validation kernels; here it must merely not index out of bounds
         const uint32_t slot1 = perm1 ? perm1[t * P.n1 + j] : j;
-        const int32_t slot2 = P.slot2_of_1[slot1];
-        if (slot2 >= 0) {
-            const uint32_t pos2 = inv2 ? inv2[t * P.n2 + (uint32_t)slot2] : (uint32_t)slot2;
-            v = P.dslot2[pos2];
+        if (slot1 < P.n1) {
+            const int32_t slot2 = slot2_base[slot1];
+            if (slot2 >= 0 && (uint32_t)slot2 < P.n2) {
+                const uint32_t pos2 = inv2 ? inv2[t * P.n2 + (uint32_t)slot2] : (uint32_t)slot2;
+                if (pos2 < P.n2) v = P.dslot2[pos2];
+            }
         }
     }
     pb[idx] = v;
@@ -575,8 +584,8 @@ __global__ void compose_pairing_kernel(const Problem P, const uint32_t *__restri
 // =====================================================================================================
 struct __align__(16) Cand {
     uint32_t ij;  // row << 16 | column
-    uint32_t k;   // overlap | kRefinedBit
-    double v;     // log lower bound of p
+    uint32_t k;   // overlap | kRefinedBit | kEvalBit
+    double v;     // log lower bound of p; once kEvalBit is set: the exact p-value
 };
 
 template <int CH>
@@ -591,20 +600,22 @@ struct ScanLayout {
     static constexpr size_t per_warp = d_bytes + q_bytes + 16 + (size_t)CAP * sizeof(Cand) + ring_bytes;
 };
 
-// Running exact optimum of one lane / one warp, with the "near tie" witness: some OTHER (K, n, k) whose p lies
-// within 1e-12 relative of the optimum (the reference's pick between such cells hangs on the last ulp of its exp()).
-struct Exact {
-    Best best;
-    bool near;
-};
-
 // Per-warp state of the rare path (everything behind the screen).  Lives in local memory on purpose: the row loop
 // touches none of it, so its registers stay free for the 2 x CH column state.
+//
+// Exact ties: the reference picks its optimum with `==` / `<` on p-values computed with the HOST libm's exp()
+// (optimize_main.rs:73-80).  The device's exp() may differ from it in the last ulp, so the device never decides between
+// two cells whose p-values are closer than the ambiguity window (kTieRel / kTieAbs, dto_host_math.hpp) unless their
+// (K, n, k) are equal (then both sides compute identical bits and the integer tie-break is exact).  Instead the cells
+// inside the window of the running minimum -- the "tie set" -- stay in the candidate buffer, already evaluated, and at the
+// end of the task a tie set with more than one distinct (K, n, k) is shipped to the host (TieEntry pool), which
+// re-evaluates it in statrs order with the host libm and applies the reference's tie-break (dto_engine.cu).
 struct Rare {
     double theta;  // certified: log(min p of the reference) <= theta
-    Exact ex;      // per-lane running optimum over everything evaluated exactly so far
-    Best zero;     // best cell on the underflow plateau (reference p == 0.0)
+    double pmin;   // smallest non-zero exact p seen so far (warp-uniform); +inf = none
+    Best zero;     // per lane: best cell on the underflow plateau (reference p == 0.0), integer tie-break only
     uint32_t ncand;
+    uint32_t overflow;  // the tie set outgrew the buffer: the task is re-run through the dense path
     uint32_t n_level2, n_eval, n_refine;
     const uint32_t *s_c1;
     uint32_t *Qij;
@@ -614,24 +625,8 @@ struct Rare {
     int lane;
 };
 
-__device__ __forceinline__ bool close_not_same(const Problem &P, const uint32_t *s_c1, const Best &a, const Best &b) {
-    if (a.ij == 0xFFFFFFFFu || b.ij == 0xFFFFFFFFu) return false;
-    if (a.p == 0.0 && b.p == 0.0) return false;  // exact ties at 0.0 are settled by the integer tie-break
-    if (fabs(a.p - b.p) > 1e-12 * fmax(a.p, b.p)) return false;
-    const bool same = (a.k == b.k) && (s_c1[a.ij >> 16] == s_c1[b.ij >> 16]) && (P.c2[a.ij & 0xFFFFu] == P.c2[b.ij & 0xFFFFu]);
-    return !same;
-}
-
-__device__ __forceinline__ void merge_exact(const Problem &P, const uint32_t *s_c1, Exact &acc, const Best &b, bool b_near) {
-    const bool close = close_not_same(P, s_c1, acc.best, b);
-    if (better(b, acc.best)) {
-        acc.near = b_near || close;
-        acc.best = b;
-    } else {
-        acc.near = acc.near || close;
-    }
-}
-
+// drops buffered candidates that can no longer be within kRefineEps of the minimum; evaluated entries (the tie set) are
+// only ever filtered by evaluate_buffer
 __device__ __noinline__ void compact_cands(Rare &R) {
     const int lane = R.lane;
     Cand *c = R.cand;
@@ -645,7 +640,7 @@ __device__ __noinline__ void compact_cands(Rare &R) {
         bool keep = false;
         if (idx < n) {
             e = c[idx];
-            keep = (e.v - kEps <= theta);
+            keep = (e.k & kEvalBit) || (e.v - kEps <= theta);
         }
         const unsigned bal = __ballot_sync(kFull, keep);
         __syncwarp();
@@ -680,34 +675,102 @@ __device__ __noinline__ void refine_buffer(const Problem &P, Rare &R) {
             d += 1.0;
         }
         const double lp = s + log(S);
-        c.v = lp - kRefineEps + kEps;
+        c.v = lp - P.refine_eps + kEps;
         c.k |= kRefinedBit;
         R.cand[idx] = c;
-        th = fmin(th, lp + kRefineEps);
+        th = fmin(th, lp + P.refine_eps);
         ++R.n_refine;
     }
     R.theta = fmin(R.theta, warp_min(th));
     __syncwarp();
 }
 
-// (4) statrs-order FP64 tail for every buffered candidate, one per lane; empties the buffer and tightens theta to
-//     the exact minimum seen so far
+// (4) statrs-order FP64 tail for every buffered candidate not evaluated yet, one per lane; tightens theta to the exact
+//     minimum seen so far and shrinks the buffer to the tie set of that minimum (entries keep their exact p in `v`)
 __device__ __noinline__ void evaluate_buffer(const Problem &P, Rare &R) {
-    double th = CUDART_INF;
-    for (uint32_t idx = R.lane; idx < R.ncand; idx += 32) {
-        const Cand c = R.cand[idx];
-        const uint32_t i = c.ij >> 16, j = c.ij & 0xFFFFu;
-        Best b;
-        b.k = c.k & ~kRefinedBit;
-        b.p = hypergeom_pvalue_exact(P.lf, P.N, R.s_c1[i], P.c2[j], b.k);
-        b.ij = c.ij;
-        merge_exact(P, R.s_c1, R.ex, b, false);
-        th = fmin(th, b.p > 0.0 ? log(b.p) + kEps : kZeroHi);
-        ++R.n_eval;
+    const int lane = R.lane;
+    Cand *c = R.cand;
+    const uint32_t n = R.ncand;
+    double mn = CUDART_INF;
+    bool sawzero = false;
+    for (uint32_t idx = lane; idx < n; idx += 32) {
+        Cand e = c[idx];
+        if (!(e.k & kEvalBit)) {
+            const uint32_t i = e.ij >> 16, j = e.ij & 0xFFFFu, k = e.k & kOverlapMask;
+            e.v = hypergeom_pvalue_exact(P.lf, P.N, R.s_c1[i], P.c2[j], k);
+            e.k = k | kEvalBit | kRefinedBit;
+            c[idx] = e;
+            ++R.n_eval;
+            if (!(e.v > 0.0)) {  // underflow plateau: exactly 0.0 in the reference too -> integer tie-break
+                Best z;
+                z.p = 0.0;
+                z.k = k;
+                z.ij = e.ij;
+                if (better(z, R.zero)) R.zero = z;
+                sawzero = true;
+            }
+        }
+        if (e.v > 0.0) mn = fmin(mn, e.v);
     }
-    R.theta = fmin(R.theta, warp_min(th));
-    R.ncand = 0;
-    __syncwarp();
+    const double pmin = fmin(R.pmin, warp_min(mn));
+    R.pmin = pmin;
+    double th = pmin < CUDART_INF ? log(pmin) + kEps : CUDART_INF;
+    if (__any_sync(kFull, sawzero)) th = fmin(th, kZeroHi);
+    R.theta = fmin(R.theta, th);
+    // keep the tie set: evaluated, non-zero, inside the ambiguity window of the minimum (same index <-> lane mapping as
+    // the loop above, so every lane re-reads only what it wrote itself)
+    uint32_t out = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    const double lim = pmin * (1.0 + kTieRel) + kTieAbs;
+    for (uint32_t b = 0; b < n; b += 32) {
+        const uint32_t idx = b + lane;
+        Cand e;
+        bool keep = false;
+        if (idx < n) {
+            e = c[idx];
+            keep = e.v > 0.0 && e.v <= lim;
+        }
+        const unsigned bal = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) c[out + __popc(bal & lt)] = e;
+        out += __popc(bal);
+        __syncwarp();
+    }
+    if (out > 4) {
+        // Lists whose ranks have gaps give equal set sizes at consecutive thresholds, hence cells with the same (K, n, k):
+        // bit-identical p on host and device alike, so among them only the smallest (row, column) can win -- drop the rest
+        // (keeps the tie set at the number of DISTINCT (K, n, k) in the window).  out <= kCandCap = 64: two entries per lane.
+        bool kp[2] = {false, false};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t idx = (uint32_t)h * 32 + lane;
+            if (idx < out) {
+                const Cand e = c[idx];
+                const uint32_t K = R.s_c1[e.ij >> 16], nn = P.c2[e.ij & 0xFFFFu];
+                bool dominated = false;
+                for (uint32_t y = 0; y < out && !dominated; ++y) {
+                    const Cand f = c[y];
+                    dominated = f.ij < e.ij && f.k == e.k && R.s_c1[f.ij >> 16] == K && P.c2[f.ij & 0xFFFFu] == nn;
+                }
+                kp[h] = !dominated;
+            }
+        }
+        __syncwarp();
+        uint32_t out2 = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t idx = (uint32_t)h * 32 + lane;
+            Cand e;
+            if (idx < out) e = c[idx];
+            const unsigned bal = __ballot_sync(kFull, kp[h]);
+            __syncwarp();
+            if (kp[h]) c[out2 + __popc(bal & lt)] = e;
+            out2 += __popc(bal);
+            __syncwarp();
+        }
+        out = out2;
+    }
+    R.ncand = out;
 }
 
 // (3a) drains the queue of cells that passed the critical-overlap screen, 32 at a time: table lookup of log p (or,
@@ -737,8 +800,8 @@ __device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, i
             if (dk < (meta.y >> 16)) {
                 // tabulated: log p of this (cell, k) to ~1e-10, no arithmetic at all
                 const double lp = P.lptab[meta.x + dk];
-                ub = lp + kRefineEps - kEps;
-                e.v = lp - kRefineEps + kEps;
+                ub = lp + P.refine_eps - kEps;
+                e.v = lp - P.refine_eps + kEps;
                 e.k |= kRefinedBit;
                 keep = true;
             } else if (k < (meta.y & 0xFFFFu)) {
@@ -761,7 +824,7 @@ __device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, i
                 } else {
                     double lb = s;  // p >= pmf(k)
                     if (r1 < 1.0) {
-                        ub = s - log1p(-r1);  // ratios fall with k: p <= pmf(k) / (1 - r1)
+                        ub = s - log1p(-r1) + P.refine_eps;  // ratios fall with k: p <= pmf(k) / (1 - r1)
                         // ratios over the next mm steps are all >= r_mm: p >= pmf * (1 - r^(mm+1)) / (1 - r)
                         double mm = floor(2.0 / (1.0 - r1)) + 1.0;
                         mm = fmin(mm, fmin(a, b));
@@ -770,7 +833,7 @@ __device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, i
                             if (rm > 0.0 && rm < 1.0) lb = s + log((1.0 - exp((mm + 1.0) * log(rm))) / (1.0 - rm));
                         }
                     }
-                    e.v = lb;
+                    e.v = lb - P.refine_eps;  // log pmf itself carries the table's rounding (ulp(lf[N]) for huge populations)
                     keep = true;
                 }
             }
@@ -785,6 +848,10 @@ __device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, i
                 compact_cands(R);
             }
             if (R.ncand + __popc(bal) > (uint32_t)kCandCap) evaluate_buffer(P, R);  // genuinely full of near-ties
+            if (R.ncand + __popc(bal) > (uint32_t)kCandCap) {  // a tie set of > 32 cells: hand the task to the dense path
+                R.overflow = 1u;
+                R.ncand = 0;
+            }
             keep = keep && (e.v - kEps <= R.theta);
         }
         const unsigned bal2 = __ballot_sync(kFull, keep);
@@ -803,7 +870,7 @@ __device__ __noinline__ int drain_queue(const Problem &P, Rare &R, bool flush, i
 
 // (5) end of a permutation: settle what is left, warp-shuffle argmin with the reference tie-break, write the record
 __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, int level, uint32_t record_flags,
-                                         dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
+                                         dto_b200_record *__restrict__ out, const ScanOut &O,
                                          unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats,
                                          long long t_begin) {
     const int lane = R.lane;
@@ -812,21 +879,67 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
     refine_buffer(P, R);
     compact_cands(R);
     evaluate_buffer(P, R);
-    merge_exact(P, R.s_c1, R.ex, R.zero, false);
-    Exact ex = R.ex;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        Best o;
-        o.p = __shfl_xor_sync(kFull, ex.best.p, off);
-        o.k = __shfl_xor_sync(kFull, ex.best.k, off);
-        o.ij = __shfl_xor_sync(kFull, ex.best.ij, off);
-        const bool o_near = __shfl_xor_sync(kFull, (int)ex.near, off) != 0;
-        merge_exact(P, R.s_c1, ex, o, o_near);
+    // the buffer now holds the tie set of the smallest non-zero p; R.zero the best cell of the underflow plateau
+    const Best zero = warp_best(R.zero);
+    const uint32_t nt = R.ncand;
+    Best mine;
+    mine.p = CUDART_INF;
+    mine.k = 0;
+    mine.ij = 0xFFFFFFFFu;
+    for (uint32_t idx = lane; idx < nt; idx += 32) {
+        const Cand c = R.cand[idx];
+        Best b;
+        b.p = c.v;
+        b.k = c.k & kOverlapMask;
+        b.ij = c.ij;
+        if (better(b, mine)) mine = b;
     }
-    const Best best = ex.best;
-    if (best.ij == 0xFFFFFFFFu || !(best.p < 1.0)) {
-        // no cell beats the cells the reference short-circuits to p = 1.0: needs the dense path
-        if (lane == 0) status[task] = 2;
+    Best best = warp_best(mine);
+    bool dense = R.overflow != 0u;
+    bool ship = false;
+    if (zero.ij != 0xFFFFFFFFu) {
+        // a cell that is exactly 0.0 on both sides beats every non-zero p -- unless that p is itself a handful of
+        // subnormal quanta, where host and device may disagree on which cells are zero at all
+        if (R.pmin <= kTieAbs) dense = true;
+        best = zero;
+    } else if (best.ij == 0xFFFFFFFFu || !(best.p < 1.0)) {
+        dense = true;  // no cell beats the cells the reference short-circuits to p = 1.0: needs the dense path
+    } else if (nt > 1) {
+        // more than one cell inside the ambiguity window: harmless iff all of them are the same (K, n, k)
+        const uint32_t bK = R.s_c1[best.ij >> 16], bn = P.c2[best.ij & 0xFFFFu];
+        bool differs = false;
+        for (uint32_t idx = lane; idx < nt; idx += 32) {
+            const Cand c = R.cand[idx];
+            differs = differs || (c.k & kOverlapMask) != best.k || R.s_c1[c.ij >> 16] != bK || P.c2[c.ij & 0xFFFFu] != bn;
+        }
+        ship = __any_sync(kFull, differs);
+    }
+    if (ship) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&O.summary->n_tie_entries, nt);
+        base = __shfl_sync(kFull, base, 0);
+        if (base + nt > O.tie_cap) {
+            // pool exhausted: the dense path settles this task; the part of the reservation that lies inside the pool is
+            // marked void so the host does not read stale entries there
+            dense = true;
+            for (uint32_t idx = lane; idx < nt; idx += 32)
+                if (base + idx < O.tie_cap) O.ties[base + idx].task = 0xFFFFFFFFu;
+        } else {
+            for (uint32_t idx = lane; idx < nt; idx += 32) {
+                const Cand c = R.cand[idx];
+                TieEntry t;
+                t.task = (uint32_t)task;
+                t.ij = c.ij;
+                t.k = c.k & kOverlapMask;
+                O.ties[base + idx] = t;
+            }
+        }
+    }
+    if (dense) {
+        if (lane == 0) {
+            O.full_list[atomicAdd(&O.summary->n_full, 1u)] = (uint32_t)task;
+            atomicAdd(&O.summary->n_done, 1u);
+        }
         __syncwarp();
         return;
     }
@@ -838,11 +951,11 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
         r.set1_len = R.s_c1[bi];
         r.set2_len = P.c2[bj];
         r.intersection_size = best.k;
-        r.flags = record_flags | (ex.near ? DTO_B200_FLAG_NEAR_TIE : 0u);
+        r.flags = record_flags;  // a shipped tie set is settled by the host, which rewrites the record (TIE_RESOLVED)
         r.population_size = P.N;
         r.pvalue = best.p;
         out[task] = r;
-        status[task] = 0;
+        atomicAdd(&O.summary->n_done, 1u);
     }
     // per-lane counters -> one atomic per warp
     uint32_t ne = R.n_eval, nr = R.n_refine;
@@ -862,7 +975,8 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
             ts[2] = ne;
             ts[3] = (uint32_t)((clock64() - t_begin) >> 4);
             ts[4] = (uint32_t)level;
-            ts[5] = ts[6] = ts[7] = 0;
+            ts[5] = nt;
+            ts[6] = ts[7] = 0;
         }
     }
     __syncwarp();
@@ -1051,8 +1165,8 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
 
 template <int CH, bool SWAR>
 __global__ void __launch_bounds__(kScanThreads, (CH > 32) ? 1 : kScanCtasPerSm)
-scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, int n_tasks, uint32_t record_flags,
-            dto_b200_record *__restrict__ out, uint32_t *__restrict__ status,
+scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, int n_tasks, int n_plain,
+            uint32_t record_flags, dto_b200_record *__restrict__ out, const ScanOut O,
             unsigned long long *__restrict__ counters, uint32_t *__restrict__ task_stats) {
     using L = ScanLayout<CH>;
     constexpr int CHP = L::CHP;
@@ -1086,10 +1200,8 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
 
         Rare R;
         R.theta = CUDART_INF;
-        R.ex.best.p = CUDART_INF;
-        R.ex.best.k = 0;
-        R.ex.best.ij = 0xFFFFFFFFu;
-        R.ex.near = false;
+        R.pmin = CUDART_INF;
+        R.overflow = 0u;
         R.zero.p = 0.0;
         R.zero.k = 0;
         R.zero.ij = 0xFFFFFFFFu;
@@ -1127,7 +1239,9 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         }
         const int level = st.level;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        finish_task(P, R, task, level, record_flags, out, status, counters, task_stats, t_begin);
+        // the first n_plain tasks of a launch are unpermuted ones riding along (batched list pairs)
+        finish_task(P, R, task, level, task < n_plain ? (record_flags & ~DTO_B200_FLAG_PERMUTED) : record_flags, out, O,
+                    counters, task_stats, t_begin);
     }
 }
 
@@ -1176,7 +1290,8 @@ __global__ void full_eval_kernel(const Problem P, const uint32_t *__restrict__ H
 
 __global__ void __launch_bounds__(1024) full_argmin_kernel(const Problem P, const uint32_t *__restrict__ H,
                                                            const double *__restrict__ pv, uint32_t record_flags,
-                                                           dto_b200_record *__restrict__ out) {
+                                                           dto_b200_record *__restrict__ out,
+                                                           uint32_t *__restrict__ best_cell) {
     __shared__ Best sb[32];
     Best best;
     best.p = CUDART_INF;
@@ -1209,8 +1324,33 @@ __global__ void __launch_bounds__(1024) full_argmin_kernel(const Problem P, cons
             r.population_size = P.N;
             r.pvalue = b.p;
             *out = r;
+            if (best_cell) *best_cell = bi * (uint32_t)P.T2 + bj;
         }
     }
+}
+
+// Dense-path tie set: every cell whose device p lies inside the ambiguity window of the device minimum (plus the argmin
+// itself), as {cell, overlap}; the host re-evaluates them with its libm and applies the reference tie-break.  When the
+// minimum is exactly 0.0 the (possibly thousands of) other exact zeros are NOT listed: exp() underflows identically on
+// both sides, so among them the integer tie-break of full_argmin_kernel is already the reference's; only cells a few
+// subnormal quanta above zero are ambiguous then.
+__global__ void full_collect_kernel(const Problem P, const uint32_t *__restrict__ H, const double *__restrict__ pv,
+                                    const uint32_t *__restrict__ best_cell, uint32_t *__restrict__ count,
+                                    uint2 *__restrict__ cells_out) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= P.T1 * P.T2) return;
+    const uint32_t bc = *best_cell;
+    const double pb = pv[bc], p = pv[cell];
+    bool take = (uint32_t)cell == bc;
+    if (!take) take = pb > 0.0 ? (p <= pb * (1.0 + kTieRel) + kTieAbs) : (p > 0.0 && p <= kTieAbs);
+    if (take) cells_out[atomicAdd(count, 1u)] = make_uint2((uint32_t)cell, H[cell]);
+}
+
+// records[idx[x]] = patch[x]: host-resolved records written back into the device-resident record array
+__global__ void patch_records_kernel(const uint32_t *__restrict__ idx, const dto_b200_record *__restrict__ patch, int n,
+                                     dto_b200_record *__restrict__ records) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n) records[idx[x]] = patch[x];
 }
 
 __global__ void pvalues_kernel(const double *__restrict__ lf, const uint64_t *__restrict__ N,
@@ -1251,8 +1391,8 @@ static int max_optin_smem() {
 }
 
 template <int CH, bool SWAR>
-static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags,
-                                 dto_b200_record *out, uint32_t *status, unsigned long long *counters,
+static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tasks, int n_plain, uint32_t flags,
+                                 dto_b200_record *out, const ScanOut &status, unsigned long long *counters,
                                  uint32_t *task_stats, int grid, int warps, cudaStream_t st) {
     using L = ScanLayout<CH>;
     const size_t smem = (((size_t)P.T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * L::per_warp;
@@ -1261,7 +1401,7 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
     // may launch the same instantiation with different sizes concurrently
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
-    kern<<<grid, warps * 32, smem, st>>>(P, pb, n_tasks, flags, out, status, counters, task_stats);
+    kern<<<grid, warps * 32, smem, st>>>(P, pb, n_tasks, n_plain, flags, out, status, counters, task_stats);
     return cudaGetLastError();
 }
 
@@ -1281,14 +1421,14 @@ int pick_ch(int T2) {
     return -1;
 }
 
-cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags, dto_b200_record *out,
-                        uint32_t *status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
+cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, int n_plain, uint32_t flags, dto_b200_record *out,
+                        const ScanOut &status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
                         cudaStream_t st) {
 #define DTO_CASE(X)                                                                                                 \
     case X:                                                                                                         \
         return P.never == 0x7FFFu                                                                                   \
-                   ? launch_scan_t<X, true>(P, pb, n_tasks, flags, out, status, counters, task_stats, grid, warps, st) \
-                   : launch_scan_t<X, false>(P, pb, n_tasks, flags, out, status, counters, task_stats, grid, warps, st);
+                   ? launch_scan_t<X, true>(P, pb, n_tasks, n_plain, flags, out, status, counters, task_stats, grid, warps, st) \
+                   : launch_scan_t<X, false>(P, pb, n_tasks, n_plain, flags, out, status, counters, task_stats, grid, warps, st);
     switch (P.CH) {
         DTO_CASE(2) DTO_CASE(4) DTO_CASE(8) DTO_CASE(12) DTO_CASE(16) DTO_CASE(20) DTO_CASE(24)
         DTO_CASE(28) DTO_CASE(32) DTO_CASE(48) DTO_CASE(64)
@@ -1364,9 +1504,14 @@ cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id
     return cudaGetLastError();
 }
 
-cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, int n_tasks,
-                           uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st) {
+cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, const int32_t *slot2_maps,
+                           int n_tasks, uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st) {
     const int th = 256;
+    if (perm1 || perm2) {  // an inverse slot no entry writes (duplicates elsewhere in the row) stays detectably invalid
+        const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
+        cudaError_t e = cudaMemsetAsync(inv_scratch, 0xFF, (size_t)nmax * n_tasks * 4, st);
+        if (e != cudaSuccess) return e;
+    }
     if (perm1) {  // validate perm1 is a permutation (scratch reused)
         const size_t tot = (size_t)P.n1 * n_tasks;
         invert_perm_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(perm1, P.n1, n_tasks, inv_scratch, err_flag);
@@ -1379,7 +1524,7 @@ cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32
     }
     const size_t tot = (size_t)P.pb_stride * n_tasks;
     compose_pairing_kernel<<<(unsigned)((tot + th - 1) / th), th, 0, st>>>(P, perm1, perm2 ? inv_scratch : nullptr,
-                                                                         n_tasks, pb);
+                                                                         slot2_maps, n_tasks, pb);
     return cudaGetLastError();
 }
 
@@ -1395,8 +1540,23 @@ cudaError_t launch_full_grid(const Problem &P, const uint16_t *pbrow, uint32_t *
 }
 
 cudaError_t launch_full_argmin(const Problem &P, const uint32_t *H, const double *pv, uint32_t flags,
-                               dto_b200_record *out, cudaStream_t st) {
-    full_argmin_kernel<<<1, 1024, 0, st>>>(P, H, pv, flags, out);
+                               dto_b200_record *out, uint32_t *best_cell, cudaStream_t st) {
+    full_argmin_kernel<<<1, 1024, 0, st>>>(P, H, pv, flags, out, best_cell);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_full_collect(const Problem &P, const uint32_t *H, const double *pv, const uint32_t *best_cell,
+                                uint32_t *count, uint2 *cells_out, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    full_collect_kernel<<<(P.T1 * P.T2 + 255) / 256, 256, 0, st>>>(P, H, pv, best_cell, count, cells_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_patch_records(const uint32_t *idx, const dto_b200_record *patch, int n, dto_b200_record *records,
+                                 cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    patch_records_kernel<<<(n + 127) / 128, 128, 0, st>>>(idx, patch, n, records);
     return cudaGetLastError();
 }
 

@@ -31,15 +31,19 @@ cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *coun
 cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *meta, double *lptab, cudaStream_t st);
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
                               uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit, int grid, cudaStream_t st);
-cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, int n_tasks,
-                           uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st);
-cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, uint32_t flags, dto_b200_record *out,
-                        uint32_t *status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
+cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, const int32_t *slot2_maps,
+                           int n_tasks, uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st);
+cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, int n_plain, uint32_t flags, dto_b200_record *out,
+                        const ScanOut &status, unsigned long long *counters, uint32_t *task_stats, int grid, int warps,
                         cudaStream_t st);
 cudaError_t launch_full_grid(const Problem &P, const uint16_t *pbrow, uint32_t *H, double *pv, double *logp,
                              cudaStream_t st);
 cudaError_t launch_full_argmin(const Problem &P, const uint32_t *H, const double *pv, uint32_t flags,
-                               dto_b200_record *out, cudaStream_t st);
+                               dto_b200_record *out, uint32_t *best_cell, cudaStream_t st);
+cudaError_t launch_full_collect(const Problem &P, const uint32_t *H, const double *pv, const uint32_t *best_cell,
+                                uint32_t *count, uint2 *cells_out, cudaStream_t st);
+cudaError_t launch_patch_records(const uint32_t *idx, const dto_b200_record *patch, int n, dto_b200_record *records,
+                                 cudaStream_t st);
 cudaError_t launch_pvalues(const double *lf, const uint64_t *N, const uint64_t *K, const uint64_t *n,
                            const uint64_t *k, size_t count, double *out, cudaStream_t st);
 cudaError_t launch_fp64_probe(double *out, int blocks, int threads, int iters, cudaStream_t st);

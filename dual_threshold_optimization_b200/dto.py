@@ -24,14 +24,14 @@ class OptimizationResultRecord:
     intersection_size: int
     pvalue: float
     permuted: bool
-    near_tie: bool = False
+    tie_resolved: bool = False  # DTO_B200_FLAG_TIE_RESOLVED: the host libm settled the optimum among ulp-close cells
 
     @staticmethod
     def from_np(r) -> "OptimizationResultRecord":
         return OptimizationResultRecord(
             int(r["rank1"]), int(r["rank2"]), int(r["set1_len"]), int(r["set2_len"]), int(r["population_size"]),
             int(r["intersection_size"]), float(r["pvalue"]), bool(int(r["flags"]) & capi.FLAG_PERMUTED),
-            bool(int(r["flags"]) & capi.FLAG_NEAR_TIE),
+            bool(int(r["flags"]) & capi.FLAG_TIE_RESOLVED),
         )
 
 
@@ -41,7 +41,7 @@ def records_to_array(results) -> np.ndarray:
     arr = np.zeros(len(results), dtype=capi.RECORD_DTYPE)
     for i, r in enumerate(results):
         arr[i] = (r.rank1, r.rank2, r.set1_len, r.set2_len, r.intersection_size,
-                  (capi.FLAG_PERMUTED if r.permuted else 0) | (capi.FLAG_NEAR_TIE if r.near_tie else 0),
+                  (capi.FLAG_PERMUTED if r.permuted else 0) | (capi.FLAG_TIE_RESOLVED if r.tie_resolved else 0),
                   r.population_size, r.pvalue)
     return arr
 

@@ -46,10 +46,18 @@ typedef struct dto_b200_record {
     double pvalue; /* statrs-order upper-tail hypergeometric p */
 } dto_b200_record;
 
-#define DTO_B200_FLAG_PERMUTED 0x1u  /* record.permuted */
-#define DTO_B200_FLAG_NEAR_TIE 0x2u  /* another cell with different (K,n,k) lies within 1e-12 relative of the minimum: the \
-                                        reference's pick between them is decided by last-ulp noise of its libm exp() */
-#define DTO_B200_FLAG_PATH_FULL 0x8u /* solved by the full-grid exact pipeline */
+#define DTO_B200_FLAG_PERMUTED 0x1u     /* record.permuted */
+/* Exactness of the optimum.  The reference chooses it with `==` / `<` on p-values computed with the HOST libm's exp()
+ * (optimize_main.rs:73-80); the device's exp() may differ from it in the last ulp.  The device therefore never decides
+ * between two cells whose p-values are closer than 1e-12 relative (+1e-320 absolute) unless their (K, n, k) are equal:
+ * such a tie set is re-evaluated on the host in statrs order with the host libm, and the reference's tie-break (largest
+ * overlap, then smallest rank1, rank2) is applied to those values.  Every record therefore carries the threshold pair the
+ * reference computes on this machine; TIE_RESOLVED merely reports that the host had to settle it. */
+#define DTO_B200_FLAG_TIE_RESOLVED 0x2u
+#define DTO_B200_FLAG_HOST_PVALUE 0x4u  /* pvalue was evaluated on the host (bit-identical to the reference's on this \
+                                           machine); otherwise on the device: same statrs operation order, CUDA exp(), \
+                                           within ~1e-14 relative */
+#define DTO_B200_FLAG_PATH_FULL 0x8u    /* solved by the full-grid exact pipeline */
 
 typedef struct dto_b200_ctx dto_b200_ctx;
 
@@ -110,7 +118,8 @@ int dto_b200_grid_debug(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t
                         double *pvalue_out, double *logp_out);
 
 /* standalone device evaluation of hypergeometric_pvalue for `count` (N,K,n,k) quadruples
- * (src/stat_operations/hypergeometric_pvalue.rs:33-50); NaN where the reference panics. */
+ * (src/stat_operations/hypergeometric_pvalue.rs:33-50); DTO_B200_ERR_PANIC where Hypergeometric::new panics
+ * (successes or draws larger than the population, :40-41). */
 int dto_b200_hypergeometric_pvalues(dto_b200_ctx *ctx, const uint64_t *N, const uint64_t *K, const uint64_t *n,
                                     const uint64_t *k, size_t count, double *pvalue_out);
 
@@ -130,6 +139,8 @@ typedef struct dto_b200_stats {
     uint64_t lptab_entries;     /* size of the per-problem log-p lookup table (8 B each) */
     uint64_t table_cache_hits;  /* set_problem calls that reused the previous problem's screen / log-p tables (same
                                  * population and set sizes per threshold; option "table_cache" = 0 disables) */
+    uint64_t tasks_tie_resolved; /* tasks whose optimum was settled on the host (DTO_B200_FLAG_TIE_RESOLVED) */
+    uint64_t tie_cells_host;     /* cells re-evaluated on the host for that */
 } dto_b200_stats;
 int dto_b200_get_stats(dto_b200_ctx *ctx, dto_b200_stats *out);
 int dto_b200_reset_stats(dto_b200_ctx *ctx);
@@ -145,7 +156,7 @@ int dto_b200_last_batch_task_stats(dto_b200_ctx *ctx, uint32_t *out, size_t max_
 int dto_b200_table_logp(dto_b200_ctx *ctx, const uint32_t *row, const uint32_t *col, const uint32_t *k, size_t count,
                         double *logp_out);
 
-/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" and "packed_screen" (before set_problem),
+/* tunables: "batch" (permutations per launch), "warps_per_cta", "levels" (2..32) and "packed_screen" (before set_problem),
  * "task_stats", "table_cache" (1 = reuse the screen / log-p tables of the previous problem when population and set sizes
  * per threshold are equal, the default; 0 = always rebuild) */
 int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value);
@@ -209,7 +220,9 @@ typedef struct dto_b200_final_result { /* the JSON object of empirical_pvalue.rs
     uint64_t rank1, rank2, set1_len, set2_len, population_size, unpermuted_intersection_size;
     double unpermuted_pvalue, empirical_pvalue, fdr;
 } dto_b200_final_result;
-/* empirical_pvalue (src/stat_operations/empirical_pvalue.rs:109-187) */
+/* empirical_pvalue (src/stat_operations/empirical_pvalue.rs:109-187).  The count of permuted p <= unpermuted p is the
+ * reference's: a permuted record whose p lies within 1e-12 relative of the unpermuted one is compared through host
+ * re-evaluations of both (statrs order, host libm), never through device-vs-host last-ulp noise. */
 int dto_b200_empirical_pvalue(const dto_b200_record *records, size_t n, dto_b200_final_result *out);
 /* serde_json::to_string_pretty of that object (src/main.rs:165): alphabetical keys, 2-space indent, shortest
  * round-trip floats.  Writes at most cap bytes incl. NUL; returns needed length in *len_out. */
@@ -217,9 +230,10 @@ int dto_b200_final_result_json(const dto_b200_final_result *r, char *buf, size_t
 
 /* Batched list-pair driver (BASELINE config 4: e.g. 2 000 TF binding x perturbation pairs): pair q is the whole CLI run
  * of src/main.rs:91-165 on (lists1[q], lists2[q], populations[q]) -- one unpermuted task + `permutations` permuted tasks
- * + empirical_pvalue -- and yields results_out[q].  Pairs shard over `devices` (contiguous chunks); pair q draws its
- * permutations from Philox seed  seed + q * 0x9E3779B97F4A7C15  with ids 0..permutations-1, so results do not depend
- * on the device list. */
+ * + empirical_pvalue -- and yields results_out[q].  Pairs shard over `devices` (contiguous chunks).  Pair q is exactly
+ * dto_b200_run_single_node on tasks [unpermuted, permuted x permutations] with seed  seed + q * 0x9E3779B97F4A7C15
+ * (permuted task t = 1..permutations uses Philox id t), so pair 0 reproduces the CLI run with the same --seed and no
+ * result depends on the device list. */
 int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200_ranked_list *const *lists2,
                        const uint64_t *populations, size_t n_pairs, size_t permutations, const int *devices,
                        size_t n_devices, uint64_t seed, dto_b200_final_result *results_out);

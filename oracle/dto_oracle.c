@@ -721,3 +721,66 @@ int oracle_run_single_node_sampled(const char *const *ids1, const uint32_t *rank
     free(jobs); free(th); free(lf); free(thr1); free(thr2);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch form of oracle_grid_int for the deep parity tests: P permuted tasks with caller-supplied indices
+ * (perm1: P x n1, perm2: P x n2, row-major; permuted.rs:56-60,90-101 semantics), spread over OS threads the way
+ * run/single_node.rs:94-133 spreads tasks.  results_out[t] = the Best record of task t (optimize_main.rs:73-116).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint32_t *ranks1, *thr1, *ranks2, *thr2;
+    size_t n1, T1, n2, T2;
+    const int32_t *slot2_of_1;
+    const uint32_t *perm1, *perm2;
+    uint64_t population;
+    const double *lf;
+    size_t begin, end;
+    oracle_record_t *results;
+    int rc;
+} batch_job_t;
+
+static void *batch_main(void *arg) {
+    batch_job_t *J = (batch_job_t *)arg;
+    for (size_t t = J->begin; t < J->end; ++t) {
+        int rc = oracle_grid_int(J->ranks1, J->n1, J->thr1, J->T1, J->ranks2, J->n2, J->thr2, J->T2, J->slot2_of_1,
+                                 J->perm1 + t * J->n1, J->perm2 + t * J->n2, 1, J->population, J->lf, NULL, NULL, NULL,
+                                 &J->results[t]);
+        if (rc) {
+            J->rc = rc;
+            break;
+        }
+    }
+    return NULL;
+}
+
+int oracle_grid_int_batch(const uint32_t *ranks1, size_t n1, const uint32_t *thr1, size_t T1,
+                          const uint32_t *ranks2, size_t n2, const uint32_t *thr2, size_t T2,
+                          const int32_t *slot2_of_1, const uint32_t *perm1, const uint32_t *perm2, size_t P,
+                          uint64_t population, const double *lf, size_t num_threads, oracle_record_t *results_out) {
+    if (P == 0) return 0;
+    if (num_threads == 0) num_threads = 1;
+    if (num_threads > P) num_threads = P;
+    size_t chunk = (P + num_threads - 1) / num_threads;
+    size_t n_chunks = (P + chunk - 1) / chunk;
+    batch_job_t *jobs = (batch_job_t *)calloc(n_chunks, sizeof(batch_job_t));
+    pthread_t *th = (pthread_t *)calloc(n_chunks, sizeof(pthread_t));
+    for (size_t c = 0; c < n_chunks; ++c) {
+        batch_job_t *J = &jobs[c];
+        J->ranks1 = ranks1; J->n1 = n1; J->thr1 = thr1; J->T1 = T1;
+        J->ranks2 = ranks2; J->n2 = n2; J->thr2 = thr2; J->T2 = T2;
+        J->slot2_of_1 = slot2_of_1; J->perm1 = perm1; J->perm2 = perm2;
+        J->population = population; J->lf = lf;
+        J->begin = c * chunk;
+        J->end = (c + 1) * chunk < P ? (c + 1) * chunk : P;
+        J->results = results_out; J->rc = 0;
+        pthread_create(&th[c], NULL, batch_main, J);
+    }
+    int rc = 0;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        pthread_join(th[c], NULL);
+        if (jobs[c].rc) rc = jobs[c].rc;
+    }
+    free(jobs);
+    free(th);
+    return rc;
+}

@@ -95,6 +95,13 @@ int oracle_grid_int(const uint32_t *ranks1, size_t n1, const uint32_t *thr1, siz
                     uint64_t population, const double *lf,
                     uint32_t *overlap_out, double *p_out, double *logp_out, oracle_record_t *best_out);
 
+/* P permuted tasks with caller-supplied indices (perm1: P x n1, perm2: P x n2), static chunks on num_threads OS threads
+ * (run/single_node.rs:94-133); results_out[t] = Best record of task t.  For the deep GPU parity tests. */
+int oracle_grid_int_batch(const uint32_t *ranks1, size_t n1, const uint32_t *thr1, size_t T1,
+                          const uint32_t *ranks2, size_t n2, const uint32_t *thr2, size_t T2,
+                          const int32_t *slot2_of_1, const uint32_t *perm1, const uint32_t *perm2, size_t P,
+                          uint64_t population, const double *lf, size_t num_threads, oracle_record_t *results_out);
+
 /* ---- epilogue: stat_operations/fdr.rs:29-60, stat_operations/empirical_pvalue.rs:109-187 */
 double oracle_fdr(uint64_t list1_len, uint64_t list2_len, uint64_t overlap, uint64_t population, double sensitivity);
 double oracle_empirical_pvalue(const double *permuted_minp, size_t P, double unpermuted_p);

@@ -110,6 +110,12 @@ def lib():
         i32p, u32p, u32p, C.c_int, C.c_uint64, f64p,
         u32p, f64p, f64p, recp,
     ]
+    L.oracle_grid_int_batch.restype = C.c_int
+    L.oracle_grid_int_batch.argtypes = [
+        u32p, C.c_size_t, u32p, C.c_size_t,
+        u32p, C.c_size_t, u32p, C.c_size_t,
+        i32p, u32p, u32p, C.c_size_t, C.c_uint64, f64p, C.c_size_t, recp,
+    ]
     L.oracle_fdr.restype = C.c_double
     L.oracle_fdr.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double]
     L.oracle_empirical_pvalue.restype = C.c_double
@@ -314,6 +320,32 @@ def grid_int(l1, l2, population, slot2_of_1=None, perm1=None, perm2=None, lf=Non
     if rc != 0:
         raise ValueError("empty threshold list")
     return GridResult(ov, pp, lp, best.as_dict())
+
+
+def best_batch(l1, l2, population, perm1, perm2, slot2_of_1=None, lf=None, num_threads=None) -> np.ndarray:
+    """Best record (optimize_main.rs:73-116) of every permuted task given by the index rows perm1[t], perm2[t]: the
+    integer grid on `num_threads` OS threads (default: all cores).  For parity runs over thousands of permutations."""
+    import os
+
+    p1 = np.ascontiguousarray(perm1, dtype=np.uint32)
+    p2 = np.ascontiguousarray(perm2, dtype=np.uint32)
+    assert p1.ndim == 2 and p2.ndim == 2 and p1.shape[0] == p2.shape[0]
+    assert p1.shape[1] == len(l1.ids) and p2.shape[1] == len(l2.ids)
+    if slot2_of_1 is None:
+        slot2_of_1 = slot_map(l1, l2)
+    if lf is None:
+        lf = ln_factorial_table(population)
+    out = np.zeros(p1.shape[0], dtype=RECORD_DTYPE)
+    rc = lib().oracle_grid_int_batch(
+        _p(l1.ranks, C.c_uint32), len(l1.ids), _p(l1.thresholds, C.c_uint32), l1.thresholds.size,
+        _p(l2.ranks, C.c_uint32), len(l2.ids), _p(l2.thresholds, C.c_uint32), l2.thresholds.size,
+        _p(np.ascontiguousarray(slot2_of_1, dtype=np.int32), C.c_int32), _p(p1, C.c_uint32), _p(p2, C.c_uint32),
+        p1.shape[0], population, _p(lf, C.c_double), num_threads or (os.cpu_count() or 1),
+        out.ctypes.data_as(C.POINTER(Record)),
+    )
+    if rc != 0:
+        raise ValueError(f"oracle_grid_int_batch failed rc={rc}")
+    return out
 
 
 def run_single_node(l1, l2, population, task_permute, num_threads, seed=0, mode=0, slot2_of_1=None, row_stride=1) -> np.ndarray:

@@ -190,3 +190,41 @@ def test_c_abi_argument_validation():
     L.dto_b200_destroy(None)  # no-op
     L.dto_b200_ranked_list_free(None)
     L.dto_b200_feature_list_free(None)
+
+
+def test_empirical_pvalue_compares_ulp_close_values_on_the_host():
+    """empirical_pvalue.rs:160-165 counts permuted p <= unpermuted p with values of ONE evaluator.  Permuted records
+    normally carry device-evaluated p (CUDA exp, last-ulp noise): simulate that noise on records whose true p equals the
+    unpermuted one (same cell), mirrors it ((K, n, k) -> (n, K, k): mathematically equal, different bits), or sits well
+    away.  The count must be the oracle's, whatever the noise did."""
+    N = 30
+    lf = O.ln_factorial_table(N)
+    cells = [(24, 13, 12), (13, 24, 12), (20, 15, 11), (15, 20, 11), (24, 13, 11), (10, 10, 6), (12, 9, 7), (9, 12, 7)]
+    rng = np.random.default_rng(0)
+    for (Ku, nu, ku) in cells[:4]:
+        pu = O.hypergeometric_pvalue_cached(lf, N, Ku, nu, ku)
+        recs = np.zeros(1 + 400, dtype=capi.RECORD_DTYPE)
+        recs[0] = (Ku, nu, Ku, nu, ku, capi.FLAG_HOST_PVALUE, N, pu)
+        want = 0
+        for t in range(1, recs.size):
+            K, n, k = cells[int(rng.integers(0, len(cells)))]
+            p = O.hypergeometric_pvalue_cached(lf, N, K, n, k)
+            want += p <= pu
+            noisy = p
+            for _ in range(int(rng.integers(0, 4))):
+                noisy = np.nextafter(noisy, [0.0, 1.0][int(rng.integers(0, 2))])
+            recs[t] = (K, n, K, n, k, capi.FLAG_PERMUTED, N, noisy)
+        fin = empirical_pvalue_struct(recs)
+        assert fin.empirical_pvalue == want / 400.0
+        assert fin.unpermuted_pvalue == pu
+
+
+def test_oracle_batch_equals_per_task_oracle():
+    ids1, r1, ids2, r2 = H.synthetic_pair(400, 13, None)
+    o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+    p1, p2 = H.perms(400, 24, 1), H.perms(400, 24, 2)
+    b = O.best_batch(o1, o2, 400, p1, p2, num_threads=3)
+    for t in range(24):
+        ob = O.grid_int(o1, o2, 400, None, p1[t], p2[t], want_overlap=False, want_p=False).best
+        assert all(int(b[t][f]) == int(ob[f]) for f in ("rank1", "rank2", "set1_len", "set2_len", "intersection_size"))
+        assert float(b[t]["pvalue"]) == float(ob["pvalue"])
