@@ -13,31 +13,7 @@ from oracle import oracle as O  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def ids_for(n, prefix="f"):
-    return [f"{prefix}{i + 1:06d}" for i in range(n)]
-
-
-def synthetic_pair(N, seed, sigma=0.25, tied_frac=0.0):
-    """list 1: rank(i) = i+1; list 2: rank of i + Normal(0, sigma*N) (sigma=None -> pure shuffle, 0 -> identical)."""
-    rng = np.random.default_rng(seed)
-    ids = ids_for(N)
-    r1 = np.arange(1, N + 1, dtype=np.uint32)
-    if sigma is None:
-        score = rng.permutation(N).astype(np.float64)
-    else:
-        score = np.arange(N) + rng.normal(0.0, sigma * N if sigma > 0 else 0.0, N)
-    order = np.argsort(score, kind="stable")
-    r2 = np.empty(N, dtype=np.uint32)
-    r2[order] = np.arange(1, N + 1, dtype=np.uint32)
-    if tied_frac > 0:
-        # collapse a fraction of features into tie groups with `min` ranking
-        for r in (r1, r2):
-            n_groups = max(1, int(N * tied_frac / 4))
-            starts = rng.choice(np.arange(1, N - 4), size=n_groups, replace=False)
-            for s in starts:
-                sel = (r >= s) & (r < s + 4)
-                r[sel] = s
-    return ids, r1, list(ids), r2
+from dual_threshold_optimization_b200.synthetic import background_subset_pair, ids_for, synthetic_pair  # noqa: E402,F401
 
 
 def background_case(n_universe, n1, n2, seed):
