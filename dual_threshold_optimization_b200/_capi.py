@@ -131,6 +131,7 @@ SYMBOLS = {
     "dto_b200_hypergeometric_pvalues": (C.c_int, [_vp, _u64p, _u64p, _u64p, _u64p, C.c_size_t, _f64p]),
     "dto_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "dto_b200_reset_stats": (C.c_int, [_vp]),
+    "dto_b200_process_totals": (C.c_int, [_u64p]),
     "dto_b200_table_logp": (C.c_int, [_vp, _u32p, _u32p, _u32p, C.c_size_t, _f64p]),
     "dto_b200_last_batch_task_stats": (C.c_int, [_vp, _u32p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dto_b200_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
@@ -155,6 +156,14 @@ SYMBOLS = {
         C.c_int,
         [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.c_uint64, _recp],
     ),
+    "dto_b200_run_tasks": (
+        C.c_int,
+        [_vp, _vp, C.c_uint64, _u64p, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.c_uint64, _recp],
+    ),
+    "dto_b200_nccl_unique_id": (C.c_int, [_vp]),
+    "dto_b200_nccl_comm_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, C.c_int, C.c_int]),
+    "dto_b200_nccl_comm_destroy": (C.c_int, [_vp]),
+    "dto_b200_allgather_minima": (C.c_int, [_vp, _vp, _vp, _vp, C.c_size_t]),
     "dto_b200_run_pairs": (
         C.c_int,
         [C.POINTER(_vp), C.POINTER(_vp), _u64p, C.c_size_t, C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.c_uint64, C.POINTER(FinalResult)],
@@ -183,6 +192,13 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def process_totals() -> dict:
+    """{launches, h2d_bytes, d2h_bytes} of the whole process since the library was loaded (pooled contexts included)."""
+    a = (C.c_uint64 * 3)()
+    check(lib().dto_b200_process_totals(a))
+    return {"launches": int(a[0]), "h2d_bytes": int(a[1]), "d2h_bytes": int(a[2])}
 
 
 def check(rc: int) -> None:

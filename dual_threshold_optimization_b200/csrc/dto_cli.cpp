@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -21,7 +22,8 @@ static void usage(FILE *f) {
             "  -p, --permutations <PERMUTATIONS>  Number of permutations to perform [default: 1000]\n"
             "  -t, --threads <THREADS>            Accepted for compatibility; the work runs on the GPU [default: 1]\n"
             "  -m, --multi-node                   Shard permutations over all visible GPUs (replaces the MPI mode)\n"
-            "      --seed <SEED>                  Philox seed of the permutation null [default: 0]\n"
+            "      --seed <SEED>                  Philox seed of the permutation null [default: drawn from the OS, like the\n"
+            "                                     reference's thread_rng; pass a value for a reproducible null]\n"
             "  -h, --help                         Print help\n"
             "  -V, --version                      Print version\n");
 }
@@ -34,7 +36,7 @@ static int die(const char *what) {
 int main(int argc, char **argv) {
     std::string list1, list2, background;
     unsigned long long permutations = 1000, threads = 1, seed = 0;
-    bool multi = false;
+    bool multi = false, have_seed = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto value = [&](const char *name) -> const char * {
@@ -49,7 +51,10 @@ int main(int argc, char **argv) {
         else if (a == "-b" || a == "--background") background = value("--background <FILE>");
         else if (a == "-p" || a == "--permutations") permutations = strtoull(value("--permutations"), nullptr, 10);
         else if (a == "-t" || a == "--threads") threads = strtoull(value("--threads"), nullptr, 10);
-        else if (a == "--seed") seed = strtoull(value("--seed"), nullptr, 10);
+        else if (a == "--seed") {
+            seed = strtoull(value("--seed"), nullptr, 10);
+            have_seed = true;
+        }
         else if (a == "-m" || a == "--multi-node") multi = true;
         else if (a == "-h" || a == "--help") {
             usage(stdout);
@@ -68,6 +73,10 @@ int main(int argc, char **argv) {
                 list1.empty() ? "  --ranked-list1 <FILE>\n" : "", list2.empty() ? "  --ranked-list2 <FILE>\n" : "");
         usage(stderr);
         return 2;
+    }
+    if (!have_seed) {  // the reference shuffles with thread_rng (permuted.rs:58): a fresh null on every run
+        std::random_device rd;
+        seed = ((unsigned long long)rd() << 32) ^ (unsigned long long)rd();
     }
     if (threads == 0) {
         fprintf(stderr, "Warning: Number of threads cannot be 0. Setting threads to 1.\n");

@@ -3,10 +3,13 @@
 // dto::optimize -> process_threshold_pairs) with batched kernel launches.  No CPU fallback exists: every
 // entry point fails with DTO_B200_ERR_CUDA when the device is unusable.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,6 +20,10 @@
 namespace dto {
 
 thread_local std::string g_last_error;
+
+// process-wide totals over every context, pooled ones included (dto_b200_process_totals): what a caller of the host layer
+// (run_tasks / run_pairs own their contexts) can still observe about launches and copies
+std::atomic<uint64_t> g_total_launches{0}, g_total_h2d{0}, g_total_d2h{0};
 
 int fail(int code, const char *fmt, ...) {
     char buf[1024];
@@ -104,6 +111,7 @@ struct dto_b200_ctx {
     DevBuf d_slotmaps, d_seeds;  // batched list pairs: per-pair gene maps (unpermuted tasks) and per-pair Philox seeds
     PinnedBuf h_summary, h_ties, h_patch;
     std::vector<uint32_t> h_c1, h_c2, h_thr1, h_thr2;  // host copies of the current problem (tie resolution builds records)
+    std::vector<uint32_t> h_ranks1, h_ranks2;          // ... and its ranks (do two list pairs share one rank structure?)
     bool opt_task_stats = false;
     bool opt_swar = true;
     bool opt_table_cache = true;
@@ -126,6 +134,19 @@ struct dto_b200_ctx {
 };
 
 namespace {
+
+inline void count_launches(dto_b200_ctx *ctx, uint64_t n) {
+    ctx->stats.kernel_launches += n;
+    g_total_launches.fetch_add(n, std::memory_order_relaxed);
+}
+inline void count_h2d(dto_b200_ctx *ctx, uint64_t bytes) {
+    ctx->stats.h2d_bytes += bytes;
+    g_total_h2d.fetch_add(bytes, std::memory_order_relaxed);
+}
+inline void count_d2h(dto_b200_ctx *ctx, uint64_t bytes) {
+    ctx->stats.d2h_bytes += bytes;
+    g_total_d2h.fetch_add(bytes, std::memory_order_relaxed);
+}
 
 int bind(dto_b200_ctx *ctx) {
     if (!ctx) return fail(DTO_B200_ERR_INVALID, "null context");
@@ -206,7 +227,7 @@ int dense_task(dto_b200_ctx *ctx, const uint16_t *pbrow, uint32_t flags, dto_b20
     CUDA_TRY(launch_full_grid(P, pbrow, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), nullptr, ctx->stream));
     CUDA_TRY(launch_full_argmin(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), flags, d_rec, d_bc, ctx->stream));
     CUDA_TRY(launch_full_collect(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), d_bc, d_bc + 1, ctx->d_collect.as<uint2>(), ctx->stream));
-    ctx->stats.kernel_launches += 6;
+    count_launches(ctx, 6);
     ctx->stats.tasks_full += 1;
     uint32_t head[2] = {0, 0};
     CUDA_TRY(cudaMemcpyAsync(head, d_bc, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -215,7 +236,7 @@ int dense_task(dto_b200_ctx *ctx, const uint16_t *pbrow, uint32_t flags, dto_b20
     if (cnt == 0 || cnt > cells) return fail(DTO_B200_ERR_CUDA, "dense path returned an invalid tie count (%u)", cnt);
     std::vector<uint2> got(cnt);
     CUDA_TRY(cudaMemcpy(got.data(), ctx->d_collect.p, (size_t)cnt * sizeof(uint2), cudaMemcpyDeviceToHost));
-    ctx->stats.d2h_bytes += 8 + (uint64_t)cnt * sizeof(uint2);
+    count_d2h(ctx, 8 + (uint64_t)cnt * sizeof(uint2));
     std::vector<HostCell> hc(cnt);
     for (uint32_t x = 0; x < cnt; ++x) {
         hc[x].ij = ((got[x].x / (uint32_t)P.T2) << 16) | (got[x].x % (uint32_t)P.T2);
@@ -234,7 +255,7 @@ int dense_task(dto_b200_ctx *ctx, const uint16_t *pbrow, uint32_t flags, dto_b20
     if (cnt > 1) ctx->stats.tasks_tie_resolved += 1;
     if (d_dst) {
         CUDA_TRY(cudaMemcpy(d_dst, &r, sizeof(r), cudaMemcpyHostToDevice));
-        ctx->stats.h2d_bytes += sizeof(r);
+        count_h2d(ctx, sizeof(r));
     }
     if (h_out) *h_out = r;
     return DTO_B200_OK;
@@ -276,11 +297,11 @@ int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags, int n_plain = 0) {
                          ctx->d_counters.as<unsigned long long>(),
                          ctx->opt_task_stats ? ctx->d_tstats.as<uint32_t>() : nullptr, grid, warps, ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev[1], ctx->stream));
-    ctx->stats.kernel_launches += 1;
+    count_launches(ctx, 1);
     ctx->stats.last_scan_launches += 1;
     ScanSummary *sum = ctx->h_summary.as<ScanSummary>();
     CUDA_TRY(cudaMemcpyAsync(sum, ctx->d_summary.p, sizeof(ScanSummary), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += sizeof(ScanSummary);
+    count_d2h(ctx, sizeof(ScanSummary));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
@@ -297,7 +318,7 @@ int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags, int n_plain = 0) {
         TieEntry *te = ctx->h_ties.as<TieEntry>();
         CUDA_TRY(cudaMemcpyAsync(te, ctx->d_ties.p, (size_t)n_ties * sizeof(TieEntry), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        ctx->stats.d2h_bytes += (uint64_t)n_ties * sizeof(TieEntry);
+        count_d2h(ctx, (uint64_t)n_ties * sizeof(TieEntry));
         std::vector<uint32_t> idx;
         std::vector<dto_b200_record> rec;
         std::vector<HostCell> hc;
@@ -329,16 +350,16 @@ int run_tasks(dto_b200_ctx *ctx, int n, uint32_t flags, int n_plain = 0) {
         memcpy(hi, idx.data(), m * 4);
         CUDA_TRY(cudaMemcpyAsync(ctx->d_patch_rec.p, hp, m * sizeof(dto_b200_record), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_patch_idx.p, hi, m * 4, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->stats.h2d_bytes += m * (sizeof(dto_b200_record) + 4);
+        count_h2d(ctx, m * (sizeof(dto_b200_record) + 4));
         CUDA_TRY(launch_patch_records(ctx->d_patch_idx.as<uint32_t>(), ctx->d_patch_rec.as<dto_b200_record>(), (int)m,
                                       ctx->d_records.as<dto_b200_record>(), ctx->stream));
-        ctx->stats.kernel_launches += 1;
+        count_launches(ctx, 1);
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the pinned staging buffers are reused by the next launch
     }
     if (n_full) {
         std::vector<uint32_t> full(n_full);
         CUDA_TRY(cudaMemcpy(full.data(), ctx->d_full_list.p, (size_t)n_full * 4, cudaMemcpyDeviceToHost));
-        ctx->stats.d2h_bytes += (uint64_t)n_full * 4;
+        count_d2h(ctx, (uint64_t)n_full * 4);
         for (uint32_t t : full) {
             if (t >= (uint32_t)n) return fail(DTO_B200_ERR_CUDA, "dense-path list names task %u of %d", t, n);
             int rc = dense_task(ctx, ctx->d_pb.as<uint16_t>() + (size_t)t * P.pb_stride,
@@ -378,6 +399,99 @@ void trim_batch_buffers(dto_b200_ctx *ctx, size_t keep_bytes) {
     for (DevBuf *b : bufs)
         if (b->cap > keep_bytes) b->release();
 }
+
+
+// Batched list pairs (BASELINE config 4).  The problem loaded in ctx must have identical gene sets; the G pairs share its
+// rank structure (hence its screen tables and pairing inputs) and differ in which gene sits where: pair g brings its own
+// gene map slot_maps[g * n1 ..] (used by its unpermuted task only -- the null of identical gene sets does not depend on
+// the map) and its own Philox seed.  One launch of each kernel covers the G unpermuted tasks (riding through the scan
+// kernel as tasks 0 .. G-1) and the G x perms permuted ones (Philox ids 1 .. perms under seeds[g]).
+// records_out is pair-major: pair g occupies [g * (perms + 1), (g + 1) * (perms + 1)), unpermuted record first.
+int run_pair_group(dto_b200_ctx *ctx, const int32_t *slot_maps, const uint64_t *seeds, size_t G, size_t perms,
+                   dto_b200_record *records_out) {
+    int rc = need_problem(ctx);
+    if (rc) return rc;
+    if (G == 0) return DTO_B200_OK;
+    if (!slot_maps || !seeds || !records_out) return fail(DTO_B200_ERR_INVALID, "null argument");
+    const Problem &P = ctx->P;
+    if (!(P.n_common == P.n1 && P.n_common == P.n2))
+        return fail(DTO_B200_ERR_UNSUPPORTED, "pair groups need identical gene sets in both lists");
+    const size_t n = G * (perms + 1);
+    if (n > (size_t)1 << 24) return fail(DTO_B200_ERR_INVALID, "pair group too large (%zu tasks)", n);
+    const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
+    if (sigma_smem_bytes(P, B1, B2, false) > ctx->smem_optin)
+        return fail(DTO_B200_ERR_UNSUPPORTED, "pairing kernel does not fit shared memory");
+    const int sigma_grid_max = ctx->sm_count * 4;
+    CUDA_TRY(ctx->d_words.ensure((size_t)sigma_grid_max * sigma_scratch_words(P) * 4));
+    CUDA_TRY(ctx->d_pb.ensure(n * P.pb_stride * 2));
+    CUDA_TRY(ctx->d_slotmaps.ensure(G * P.n1 * 4));
+    CUDA_TRY(ctx->d_seeds.ensure(G * 8));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_slotmaps.p, slot_maps, G * P.n1 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_seeds.p, seeds, G * 8, cudaMemcpyHostToDevice, ctx->stream));
+    count_h2d(ctx, G * ((uint64_t)P.n1 * 4 + 8));
+    ctx->stats.last_scan_kernel_ms = 0;
+    ctx->stats.last_sigma_kernel_ms = 0;
+    ctx->stats.last_scan_launches = 0;
+    CUDA_TRY(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CUDA_TRY(launch_compose(P, nullptr, nullptr, ctx->d_slotmaps.as<int32_t>(), (int)G, nullptr, ctx->d_err.as<int>(),
+                            ctx->d_pb.as<uint16_t>(), ctx->stream));
+    count_launches(ctx, 1);
+    if (perms) {
+        CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
+        CUDA_TRY(launch_sigma_sort(P, 0, ctx->d_seeds.as<uint64_t>(), (uint32_t)perms, 1, (int)(G * perms),
+                                   ctx->d_pb.as<uint16_t>() + G * P.pb_stride, nullptr, ctx->d_words.as<uint32_t>(),
+                                   ctx->smem_optin, (int)std::min<size_t>(G * perms, (size_t)sigma_grid_max), ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
+        count_launches(ctx, 1);
+    }
+    rc = run_tasks(ctx, (int)n, DTO_B200_FLAG_PERMUTED, (int)G);
+    if (rc) return rc;
+    if (perms) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+        ctx->stats.last_sigma_kernel_ms += ms;
+    }
+    CUDA_TRY(ctx->h_records.ensure(n * sizeof(dto_b200_record)));
+    dto_b200_record *stage = ctx->h_records.as<dto_b200_record>();
+    CUDA_TRY(cudaMemcpyAsync(stage, ctx->d_records.p, n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    count_d2h(ctx, n * sizeof(dto_b200_record));
+    float run_ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&run_ms, ctx->ev[4], ctx->ev[5]));
+    ctx->stats.last_run_ms = run_ms;
+    for (size_t g = 0; g < G; ++g) {
+        dto_b200_record *dst = records_out + g * (perms + 1);
+        dto_b200_record u = stage[g];
+        if (!(u.flags & DTO_B200_FLAG_HOST_PVALUE)) {
+            // the unpermuted p is an output field of the run (main.rs:165): evaluate it with the host libm, as the
+            // reference does (the cell itself was settled exactly by the scan / tie resolution)
+            u.pvalue = host_p(ctx, u.set1_len, u.set2_len, u.intersection_size);
+            u.flags |= DTO_B200_FLAG_HOST_PVALUE;
+        }
+        dst[0] = u;
+        memcpy(dst + 1, stage + G + g * perms, perms * sizeof(dto_b200_record));
+    }
+    return DTO_B200_OK;
+}
+
+// The pairing inputs of a problem: what makes two list pairs batchable into one group (together with identical gene sets)
+bool same_rank_structure(const dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, const uint32_t *thr1, size_t T1,
+                         const uint32_t *ranks2, size_t n2, const uint32_t *thr2, size_t T2, uint64_t population) {
+    if (!ctx->has_problem) return false;
+    const Problem &P = ctx->P;
+    if (P.N != population || P.n1 != n1 || P.n2 != n2 || (size_t)P.T1 != T1 || (size_t)P.T2 != T2) return false;
+    if (memcmp(ctx->h_thr1.data(), thr1, T1 * 4) || memcmp(ctx->h_thr2.data(), thr2, T2 * 4)) return false;
+    return ctx->h_ranks1.size() == n1 && ctx->h_ranks2.size() == n2 && !memcmp(ctx->h_ranks1.data(), ranks1, n1 * 4) &&
+           !memcmp(ctx->h_ranks2.data(), ranks2, n2 * 4);
+}
+
+bool identical_gene_sets(const dto_b200_ctx *ctx) {
+    return ctx->has_problem && ctx->P.n_common == ctx->P.n1 && ctx->P.n_common == ctx->P.n2;
+}
+
+size_t group_task_capacity(const dto_b200_ctx *ctx) { return ctx->has_problem ? (size_t)auto_batch(ctx) : 0; }
+
 }  // namespace dto
 
 extern "C" {
@@ -476,6 +590,14 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
     } else {
         return fail(DTO_B200_ERR_INVALID, "unknown option '%s'", name);
     }
+    return DTO_B200_OK;
+}
+
+int dto_b200_process_totals(uint64_t *out3) {
+    if (!out3) return fail(DTO_B200_ERR_INVALID, "null output");
+    out3[0] = g_total_launches.load();
+    out3[1] = g_total_h2d.load();
+    out3[2] = g_total_d2h.load();
     return DTO_B200_OK;
 }
 
@@ -622,13 +744,15 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     auto up = [&](DevBuf &b, const void *src, size_t bytes) -> cudaError_t {
         cudaError_t e = b.ensure(bytes);
         if (e != cudaSuccess) return e;
-        ctx->stats.h2d_bytes += bytes;
+        count_h2d(ctx, bytes);
         return cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
     };
     ctx->h_c1 = c1;
     ctx->h_c2 = c2;
     ctx->h_thr1.assign(thr1, thr1 + T1);
     ctx->h_thr2.assign(thr2, thr2 + T2);
+    ctx->h_ranks1.assign(ranks1, ranks1 + n1);
+    ctx->h_ranks2.assign(ranks2, ranks2 + n2);
     const bool tables_cached = ctx->opt_table_cache && ctx->tab_valid && ctx->tab_N == population &&
                                ctx->tab_levels == P.levels && ctx->tab_never == P.never && ctx->tab_c1 == c1 &&
                                ctx->tab_c2 == c2;
@@ -692,9 +816,9 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.cellmeta = ctx->d_meta.as<uint2>();
     P.lptab = ctx->d_lptab.as<double>();
     CUDA_TRY(launch_fill_lptab(P, ctx->d_counts.as<uint32_t>(), ctx->d_meta.as<uint2>(), ctx->d_lptab.as<double>(), ctx->stream));
-    ctx->stats.kernel_launches += 3;
-    ctx->stats.h2d_bytes += cells * 4;
-    ctx->stats.d2h_bytes += cells * 4;
+    count_launches(ctx, 3);
+    count_h2d(ctx, cells * 4);
+    count_d2h(ctx, cells * 4);
     ctx->stats.lptab_entries = total;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     ctx->tab_N = population;
@@ -716,7 +840,7 @@ int dto_b200_run_unpermuted(dto_b200_ctx *ctx, dto_b200_record *record_out) {
     const Problem &P = ctx->P;
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
     CUDA_TRY(launch_compose(P, nullptr, nullptr, nullptr, 1, nullptr, ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
-    ctx->stats.kernel_launches += 1;
+    count_launches(ctx, 1);
     ctx->stats.last_scan_kernel_ms = 0;
     ctx->stats.last_sigma_kernel_ms = 0;
     ctx->stats.last_scan_launches = 0;
@@ -749,11 +873,11 @@ int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, cons
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_perm1.p, perm1 + done * P.n1, (size_t)n * P.n1 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(ctx->d_perm2.p, perm2 + done * P.n2, (size_t)n * P.n2 * 4, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->stats.h2d_bytes += (uint64_t)n * ((uint64_t)P.n1 + P.n2) * 4;
+        count_h2d(ctx, (uint64_t)n * ((uint64_t)P.n1 + P.n2) * 4);
         CUDA_TRY(cudaMemsetAsync(ctx->d_err.p, 0, 4, ctx->stream));
         CUDA_TRY(launch_compose(P, ctx->d_perm1.as<uint32_t>(), ctx->d_perm2.as<uint32_t>(), nullptr, n, ctx->d_inv.as<uint32_t>(),
                                 ctx->d_err.as<int>(), ctx->d_pb.as<uint16_t>(), ctx->stream));
-        ctx->stats.kernel_launches += 5;
+        count_launches(ctx, 5);
         int err = 0;
         CUDA_TRY(cudaMemcpyAsync(&err, ctx->d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -761,7 +885,7 @@ int dto_b200_run_permuted_indices(dto_b200_ctx *ctx, const uint32_t *perm1, cons
         rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpy(records_out + done, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost));
-        ctx->stats.d2h_bytes += (uint64_t)n * sizeof(dto_b200_record) + 4;
+        count_d2h(ctx, (uint64_t)n * sizeof(dto_b200_record) + 4);
     }
     return DTO_B200_OK;
 }
@@ -793,10 +917,10 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
         const int n = (int)std::min(batch, Pn - done);
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
         CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
-        CUDA_TRY(launch_sigma_sort(P, seed, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr, words_scratch,
+        CUDA_TRY(launch_sigma_sort(P, seed, nullptr, 0, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr, words_scratch,
                                    ctx->smem_optin, std::min(n, sigma_grid_max), ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
-        ctx->stats.kernel_launches += 1;
+        count_launches(ctx, 1);
         rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
         if (rc) return rc;
         float ms = 0.f;
@@ -805,7 +929,7 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
         if (h_records || h_minp) {
             dto_b200_record *stage = ctx->h_records.as<dto_b200_record>();
             CUDA_TRY(cudaMemcpyAsync(stage, ctx->d_records.p, (size_t)n * sizeof(dto_b200_record), cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->stats.d2h_bytes += (uint64_t)n * sizeof(dto_b200_record);
+            count_d2h(ctx, (uint64_t)n * sizeof(dto_b200_record));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream));
             if (h_records) memcpy(h_records + done, stage, (size_t)n * sizeof(dto_b200_record));
             if (h_minp)
@@ -850,9 +974,9 @@ int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, 
     CUDA_TRY(ctx->d_pb.ensure((size_t)P.pb_stride * 2));
     CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_pair.p, 0xFF, (size_t)(P.n1 ? P.n1 : 1) * 4, ctx->stream));
-    CUDA_TRY(launch_sigma_sort(P, seed, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), words_scratch,
+    CUDA_TRY(launch_sigma_sort(P, seed, nullptr, 0, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), words_scratch,
                                ctx->smem_optin, 1, ctx->stream));
-    ctx->stats.kernel_launches += 1;
+    count_launches(ctx, 1);
     CUDA_TRY(cudaMemcpyAsync(pos2_of_pos1_out, ctx->d_pair.p, (size_t)P.n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return DTO_B200_OK;
@@ -886,7 +1010,7 @@ int dto_b200_grid_debug(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t
     if (err) return fail(DTO_B200_ERR_INVALID, "perm1/perm2 must each be a permutation of 0..n-1");
     CUDA_TRY(launch_full_grid(P, ctx->d_pb.as<uint16_t>(), ctx->d_H.as<uint32_t>(), pvalue_out ? ctx->d_pv.as<double>() : nullptr,
                               logp_out ? ctx->d_logp.as<double>() : nullptr, ctx->stream));
-    ctx->stats.kernel_launches += 5;
+    count_launches(ctx, 5);
     if (overlap_out) CUDA_TRY(cudaMemcpyAsync(overlap_out, ctx->d_H.p, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (pvalue_out) CUDA_TRY(cudaMemcpyAsync(pvalue_out, ctx->d_pv.p, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (logp_out) CUDA_TRY(cudaMemcpyAsync(logp_out, ctx->d_logp.p, cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -929,7 +1053,7 @@ int dto_b200_hypergeometric_pvalues(dto_b200_ctx *ctx, const uint64_t *N, const 
     d_lf.release();
     d_in.release();
     d_out.release();
-    ctx->stats.kernel_launches += 1;
+    count_launches(ctx, 1);
     CUDA_TRY(e);
     return DTO_B200_OK;
 }
@@ -981,6 +1105,118 @@ int dto_b200_probe_hbm_gbs(dto_b200_ctx *ctx, double *gbs_out) {
     a.release();
     b.release();
     *gbs_out = best;
+    return DTO_B200_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Product-side collective: the all-gather of per-permutation minima that replaces the MPI gather of
+// src/run/multi_node.rs:148-160 when one process drives each GPU.  NCCL is bound at run time (dlopen of libnccl.so.2:
+// the copy already mapped by the host application if there is one, else the system's), so the library neither links
+// NCCL nor needs it when a single process drives all GPUs.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclUid {
+    char internal[128];
+};
+
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(NcclUid *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*CommCount)(void *, int *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+
+NcclApi &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) {
+            api.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return;
+        }
+        auto sym = [&](const char *name) -> void * {
+            void *p = dlsym(api.handle, name);
+            if (!p && api.why.empty()) api.why = std::string("libnccl lacks ") + name;
+            return p;
+        };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.CommCount = reinterpret_cast<decltype(api.CommCount)>(sym("ncclCommCount"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    });
+    return api;
+}
+
+int nccl_ready(NcclApi *&out) {
+    NcclApi &a = nccl_api();
+    if (!a.why.empty() || !a.handle) return fail(DTO_B200_ERR_UNSUPPORTED, "NCCL unavailable: %s", a.why.c_str());
+    out = &a;
+    return DTO_B200_OK;
+}
+
+constexpr int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 (nccl.h)
+
+}  // namespace
+
+extern "C" {
+
+int dto_b200_nccl_unique_id(void *id_out) {
+    if (!id_out) return fail(DTO_B200_ERR_INVALID, "null id_out");
+    NcclApi *a = nullptr;
+    int rc = nccl_ready(a);
+    if (rc) return rc;
+    const int e = a->GetUniqueId(reinterpret_cast<NcclUid *>(id_out));
+    if (e) return fail(DTO_B200_ERR_CUDA, "ncclGetUniqueId: %s", a->GetErrorString(e));
+    return DTO_B200_OK;
+}
+
+int dto_b200_nccl_comm_create(void **comm_out, int n_ranks, const void *unique_id, int rank, int device) {
+    if (!comm_out || !unique_id) return fail(DTO_B200_ERR_INVALID, "null argument");
+    *comm_out = nullptr;
+    NcclApi *a = nullptr;
+    int rc = nccl_ready(a);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    NcclUid uid;
+    memcpy(&uid, unique_id, sizeof(uid));
+    const int e = a->CommInitRank(comm_out, n_ranks, uid, rank);
+    if (e) return fail(DTO_B200_ERR_CUDA, "ncclCommInitRank(rank %d of %d): %s", rank, n_ranks, a->GetErrorString(e));
+    return DTO_B200_OK;
+}
+
+int dto_b200_nccl_comm_destroy(void *comm) {
+    if (!comm) return DTO_B200_OK;
+    NcclApi *a = nullptr;
+    int rc = nccl_ready(a);
+    if (rc) return rc;
+    const int e = a->CommDestroy(comm);
+    if (e) return fail(DTO_B200_ERR_CUDA, "ncclCommDestroy: %s", a->GetErrorString(e));
+    return DTO_B200_OK;
+}
+
+int dto_b200_allgather_minima(dto_b200_ctx *ctx, void *nccl_comm, const double *d_send, double *d_recv, size_t count) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!nccl_comm || (count && (!d_send || !d_recv))) return fail(DTO_B200_ERR_INVALID, "null argument");
+    NcclApi *a = nullptr;
+    rc = nccl_ready(a);
+    if (rc) return rc;
+    if (count == 0) return DTO_B200_OK;
+    const int e = a->AllGather(d_send, d_recv, count, kNcclFloat64, nccl_comm, ctx->stream);
+    if (e) return fail(DTO_B200_ERR_CUDA, "ncclAllGather: %s", a->GetErrorString(e));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    count_launches(ctx, 1);  // NCCL's own kernel; counted so that callers can tell it ran
     return DTO_B200_OK;
 }
 

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <fstream>
 #include <memory>
 #include <mutex>
@@ -353,28 +355,36 @@ int dto_b200_compute_population_size(const dto_b200_ranked_list *l1, const dto_b
     return DTO_B200_OK;
 }
 
-// string ids -> slot map (the integer form of intersect_genes.rs:38-56)
+// string ids -> slot map (the integer form of intersect_genes.rs:38-56): slot[a] = sorted slot in l2 of the gene at sorted
+// slot a of l1, or -1.  Memoised per (l1, l2).
+static int slot_map_of(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, std::vector<int32_t> &slot) {
+    {
+        std::lock_guard<std::mutex> lock(l1->memo_mu);
+        if (l1->memo_partner_uid == l2->uid && l1->memo_slot.size() == l1->ids.size() && !l1->ids.empty()) {
+            slot = l1->memo_slot;
+            return DTO_B200_OK;
+        }
+    }
+    if (l2->dup_index >= 0)
+        return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list",
+                    l2->ids[(size_t)l2->dup_index].c_str());
+    if (l1->dup_index >= 0)
+        return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list",
+                    l1->ids[(size_t)l1->dup_index].c_str());
+    slot.assign(l1->ids.size(), -1);
+    for (size_t a = 0; a < l1->ids.size(); ++a) slot[a] = find_id(l2, l1->ids[a], l1->id_hash[a]);
+    std::lock_guard<std::mutex> lock(l1->memo_mu);
+    l1->memo_partner_uid = l2->uid;
+    l1->memo_slot = slot;
+    return DTO_B200_OK;
+}
+
 int dto_b200_load_lists(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2,
                         uint64_t population) {
     if (!ctx || !l1 || !l2) return fail(DTO_B200_ERR_INVALID, "null argument");
     std::vector<int32_t> slot;
-    {
-        std::lock_guard<std::mutex> lock(l1->memo_mu);
-        if (l1->memo_partner_uid == l2->uid && l1->memo_slot.size() == l1->ids.size()) slot = l1->memo_slot;
-    }
-    if (slot.size() != l1->ids.size() || l1->ids.empty()) {
-        if (l2->dup_index >= 0)
-            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the second ranked list",
-                        l2->ids[(size_t)l2->dup_index].c_str());
-        if (l1->dup_index >= 0)
-            return fail(DTO_B200_ERR_INVALID, "duplicate feature id \"%s\" in the first ranked list",
-                        l1->ids[(size_t)l1->dup_index].c_str());
-        slot.assign(l1->ids.size(), -1);
-        for (size_t a = 0; a < l1->ids.size(); ++a) slot[a] = find_id(l2, l1->ids[a], l1->id_hash[a]);
-        std::lock_guard<std::mutex> lock(l1->memo_mu);
-        l1->memo_partner_uid = l2->uid;
-        l1->memo_slot = slot;
-    }
+    int rc = slot_map_of(l1, l2, slot);
+    if (rc) return rc;
     return dto_b200_set_problem(ctx, l1->ranks.data(), l1->ranks.size(), l1->thresholds.data(), l1->thresholds.size(),
                                 l2->ranks.data(), l2->ranks.size(), l2->thresholds.data(), l2->thresholds.size(),
                                 slot.data(), population);
@@ -392,9 +402,9 @@ int dto_b200_optimize(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const d
 // ---------------------------------------------------------------------------------------------------
 // run_single_node (src/run/single_node.rs:83-137) -- tasks sharded over GPUs instead of threads / MPI ranks
 // ---------------------------------------------------------------------------------------------------
-int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, uint64_t population,
-                             const uint8_t *task_permute, size_t n_tasks, const int *devices, size_t n_devices,
-                             uint64_t seed, dto_b200_record *records_out) {
+int dto_b200_run_tasks(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, uint64_t population,
+                       const uint64_t *task_ids, const uint8_t *task_permute, size_t n_tasks, const int *devices,
+                       size_t n_devices, uint64_t seed, dto_b200_record *records_out) {
     if (!l1 || !l2) return fail(DTO_B200_ERR_INVALID, "null list");
     if (n_tasks == 0) return DTO_B200_OK;
     if (!task_permute || !records_out) return fail(DTO_B200_ERR_INVALID, "null argument");
@@ -402,9 +412,11 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
     if (n_devices == 0 || !devices) devs.push_back(0);
     else devs.assign(devices, devices + n_devices);
 
-    // runs of consecutive permuted task ids, so each maps onto one philox id range
+    // runs of consecutive permuted tasks with consecutive ids, so each maps onto one Philox id range
     struct Run {
-        size_t first, count;
+        size_t first;    // index into the task arrays
+        uint64_t id;     // Philox id of that task
+        size_t count;
     };
     std::vector<Run> runs;
     std::vector<size_t> unperm;
@@ -415,8 +427,9 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
             continue;
         }
         ++n_perm;
-        if (!runs.empty() && runs.back().first + runs.back().count == t) runs.back().count++;
-        else runs.push_back({t, 1});
+        const uint64_t id = task_ids ? task_ids[t] : (uint64_t)t;
+        if (!runs.empty() && runs.back().first + runs.back().count == t && runs.back().id + runs.back().count == id) runs.back().count++;
+        else runs.push_back({t, id, 1});
     }
     // contiguous, near-equal shards of the permuted tasks per device (multi_node.rs:114-129 chunks by rank the same way)
     const size_t G = devs.size();
@@ -431,8 +444,9 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
                     room = per;
                 }
                 const size_t take = std::min(room, r.count);
-                shard[g].push_back({r.first, take});
+                shard[g].push_back({r.first, r.id, take});
                 r.first += take;
+                r.id += take;
                 r.count -= take;
                 room -= take;
             }
@@ -453,8 +467,7 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
                 for (size_t t : unperm) records_out[t] = r;
         }
         for (size_t x = 0; rc == DTO_B200_OK && x < shard[g].size(); ++x)
-            rc = dto_b200_run_permuted_philox(ctx, seed, (uint64_t)shard[g][x].first, shard[g][x].count,
-                                              records_out + shard[g][x].first, nullptr);
+            rc = dto_b200_run_permuted_philox(ctx, seed, shard[g][x].id, shard[g][x].count, records_out + shard[g][x].first, nullptr);
         if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
         rcs[g] = rc;
         pool_release(ctx, devs[g], rc == DTO_B200_OK);
@@ -471,25 +484,51 @@ int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_rank
     return DTO_B200_OK;
 }
 
+int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, uint64_t population,
+                             const uint8_t *task_permute, size_t n_tasks, const int *devices, size_t n_devices,
+                             uint64_t seed, dto_b200_record *records_out) {
+    return dto_b200_run_tasks(l1, l2, population, nullptr, task_permute, n_tasks, devices, n_devices, seed, records_out);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // batched list pairs: the CLI run of src/main.rs:91-165 once per pair, pairs sharded over GPUs
 // ---------------------------------------------------------------------------------------------------
+namespace {
+
+inline uint64_t pair_seed(uint64_t seed, size_t q) { return seed + (uint64_t)q * 0x9E3779B97F4A7C15ull; }
+
+// two list pairs whose lists carry the same ranks (hence thresholds, set sizes, screen tables) and whose two lists hold the
+// same genes can share one launch: only the gene map of the unpermuted task differs
+bool same_ranks(const dto_b200_ranked_list *a, const dto_b200_ranked_list *b) {
+    return a->ranks.size() == b->ranks.size() && !memcmp(a->ranks.data(), b->ranks.data(), a->ranks.size() * 4);
+}
+
+struct PairGroup {
+    size_t lo = 0, hi = 0;           // pairs [lo, hi)
+    bool batched = false;            // one launch for the whole group (else pair by pair)
+    std::vector<int32_t> slot_maps;  // batched: (hi - lo) x n1
+    std::vector<uint64_t> seeds;
+    int rc = DTO_B200_OK;
+    std::string err;
+};
+
+}  // namespace
+
 int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200_ranked_list *const *lists2,
                        const uint64_t *populations, size_t n_pairs, size_t permutations, const int *devices,
                        size_t n_devices, uint64_t seed, dto_b200_final_result *results_out) {
     if (n_pairs == 0) return DTO_B200_OK;
     if (!lists1 || !lists2 || !populations || !results_out) return fail(DTO_B200_ERR_INVALID, "null argument");
-    std::vector<int> base;
-    if (n_devices == 0 || !devices) base.push_back(0);
-    else base.assign(devices, devices + n_devices);
-    // A 1 000-permutation pair neither fills a GPU nor hides its own host-side setup (string canonicalisation,
-    // ln-factorial table, screen-table build): run several contexts per device so setup of one pair overlaps the
-    // kernels of another (measured on a B200, N = 6 000: 1 -> 4 workers = 3.3x pairs/s).  Results are per-pair pure
-    // functions of (seed, pair index), so the worker layout never changes them.
-    const size_t workers_per_device = n_pairs >= 8 * base.size() ? 4 : 1;
+    for (size_t q = 0; q < n_pairs; ++q)
+        if (!lists1[q] || !lists2[q]) return fail(DTO_B200_ERR_INVALID, "null list in pair %zu", q);
     std::vector<int> devs;
-    for (int d : base)
-        for (size_t w = 0; w < workers_per_device; ++w) devs.push_back(d);
+    if (n_devices == 0 || !devices) devs.push_back(0);
+    else devs.assign(devices, devices + n_devices);
+    // One context (one host thread driving the GPU) per device.  A 1 000-permutation pair fills a quarter of one wave of
+    // scan warps, so consecutive pairs that share their rank structure -- the common case: every list ranks the same
+    // genes 1..n -- go through ONE launch of each kernel (dto::run_pair_group); a second host thread per device prepares
+    // the next group (string ids -> gene maps) while the GPU works on the current one.  Results are per-pair pure
+    // functions of (seed, pair index), so neither the grouping nor the device list changes them.
     const size_t G = devs.size();
     const size_t per = (n_pairs + G - 1) / G;
     std::vector<int> rcs(G, DTO_B200_OK);
@@ -499,18 +538,95 @@ int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200
         if (lo >= hi) return;
         dto_b200_ctx *ctx = nullptr;
         int rc = pool_acquire(&ctx, devs[g]);
-        std::vector<dto_b200_record> recs(permutations + 1);
-        for (size_t q = lo; rc == DTO_B200_OK && q < hi; ++q) {
-            if (!lists1[q] || !lists2[q]) {
-                rc = fail(DTO_B200_ERR_INVALID, "null list in pair %zu", q);
+        if (rc != DTO_B200_OK) {
+            errs[g] = dto_b200_last_error();
+            rcs[g] = rc;
+            return;
+        }
+        // group boundaries depend on the launch capacity, which depends on the problem shape: plan with the first pair's
+        const size_t cap_tasks = (size_t)1 << 17;
+        const size_t max_group = std::min<size_t>(256, std::max<size_t>(1, cap_tasks / (permutations + 1)));
+        // producer: builds groups ahead of the GPU (bounded queue of 2)
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<std::unique_ptr<PairGroup>> ready;
+        bool done = false, abort = false;
+        std::thread producer([&]() {
+            size_t q = lo;
+            while (q < hi) {
+                auto grp = std::make_unique<PairGroup>();
+                grp->lo = q;
+                size_t e = q + 1;
+                // identical gene sets <=> every id of l1 is in l2 and the lengths agree (ids are distinct)
+                std::vector<int32_t> slot;
+                int prc = slot_map_of(lists1[q], lists2[q], slot);
+                bool ident = prc == DTO_B200_OK && lists1[q]->ids.size() == lists2[q]->ids.size() &&
+                             std::find(slot.begin(), slot.end(), -1) == slot.end() && !slot.empty();
+                if (prc != DTO_B200_OK) {
+                    grp->rc = prc;
+                    grp->err = dto_b200_last_error();
+                }
+                if (ident) {
+                    grp->batched = true;
+                    grp->slot_maps = slot;
+                    grp->seeds.push_back(pair_seed(seed, q));
+                    while (e < hi && e - q < max_group && populations[e] == populations[q] && same_ranks(lists1[e], lists1[q]) &&
+                           same_ranks(lists2[e], lists2[q])) {
+                        std::vector<int32_t> s2;
+                        if (slot_map_of(lists1[e], lists2[e], s2) != DTO_B200_OK) break;  // reported when it leads its own group
+                        if (s2.size() != slot.size() || std::find(s2.begin(), s2.end(), -1) != s2.end()) break;
+                        grp->slot_maps.insert(grp->slot_maps.end(), s2.begin(), s2.end());
+                        grp->seeds.push_back(pair_seed(seed, e));
+                        ++e;
+                    }
+                }
+                grp->hi = e;
+                q = e;
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return ready.size() < 2 || abort; });
+                if (abort) return;
+                ready.push_back(std::move(grp));
+                cv.notify_all();
+            }
+            std::lock_guard<std::mutex> lock(mu);
+            done = true;
+            cv.notify_all();
+        });
+        std::vector<dto_b200_record> recs;
+        while (rc == DTO_B200_OK) {
+            std::unique_ptr<PairGroup> grp;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv.wait(lock, [&] { return !ready.empty() || done; });
+                if (ready.empty()) break;
+                grp = std::move(ready.front());
+                ready.pop_front();
+                cv.notify_all();
+            }
+            if (grp->rc != DTO_B200_OK) {
+                rc = fail(grp->rc, "%s", grp->err.c_str());
                 break;
             }
-            rc = dto_b200_load_lists(ctx, lists1[q], lists2[q], populations[q]);
-            if (rc == DTO_B200_OK) rc = dto_b200_run_unpermuted(ctx, &recs[0]);
-            if (rc == DTO_B200_OK && permutations)
-                rc = dto_b200_run_permuted_philox(ctx, seed + (uint64_t)q * 0x9E3779B97F4A7C15ull, 1, permutations, recs.data() + 1, nullptr);
-            if (rc == DTO_B200_OK) rc = dto_b200_empirical_pvalue(recs.data(), recs.size(), &results_out[q]);
+            const size_t n = grp->hi - grp->lo;
+            rc = dto_b200_load_lists(ctx, lists1[grp->lo], lists2[grp->lo], populations[grp->lo]);
+            if (rc != DTO_B200_OK) break;
+            recs.resize(n * (permutations + 1));
+            if (grp->batched && dto::identical_gene_sets(ctx)) {
+                rc = dto::run_pair_group(ctx, grp->slot_maps.data(), grp->seeds.data(), n, permutations, recs.data());
+            } else {  // differing gene sets (background mode): pair by pair (n == 1)
+                rc = dto_b200_run_unpermuted(ctx, &recs[0]);
+                if (rc == DTO_B200_OK && permutations)
+                    rc = dto_b200_run_permuted_philox(ctx, pair_seed(seed, grp->lo), 1, permutations, recs.data() + 1, nullptr);
+            }
+            for (size_t x = 0; rc == DTO_B200_OK && x < n; ++x)
+                rc = dto_b200_empirical_pvalue(recs.data() + x * (permutations + 1), permutations + 1, &results_out[grp->lo + x]);
         }
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            abort = true;
+            cv.notify_all();
+        }
+        producer.join();
         if (rc != DTO_B200_OK) errs[g] = dto_b200_last_error();
         rcs[g] = rc;
         pool_release(ctx, devs[g], rc == DTO_B200_OK);

@@ -444,7 +444,8 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
 }
 
 template <bool BA_IN_SCRATCH>
-__global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed,
+__global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed0,
+                                                                   const uint64_t *__restrict__ seeds, uint32_t seg,
                                                                    uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
                                                                    uint32_t *__restrict__ pairing_out,
@@ -490,7 +491,9 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     }
 
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
-        const uint64_t perm_id = first_id + (uint64_t)t;
+        // batched list pairs: `seg` consecutive tasks belong to one pair, which has its own seed and ids first_id ..
+        const uint64_t seed = seeds ? seeds[(uint32_t)t / seg] : seed0;
+        const uint64_t perm_id = first_id + (uint64_t)(seeds ? (uint32_t)t % seg : (uint32_t)t);
         uint16_t *dst = pb + (size_t)t * P.pb_stride;
         if (rowwise) {
             block_place_rowwise(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
@@ -1487,8 +1490,9 @@ int pick_bucket_bits(uint32_t n) {
     return B;
 }
 
-cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id, int n_tasks, uint16_t *pb,
-                              uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit, int grid, cudaStream_t st) {
+cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, const uint64_t *seeds, uint32_t seg, uint64_t first_id,
+                              int n_tasks, uint16_t *pb, uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit,
+                              int grid, cudaStream_t st) {
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
     const bool ba_in_smem = sigma_smem_bytes(P, B1, B2, true) <= smem_limit;
     const size_t base = sigma_smem_bytes(P, B1, B2, ba_in_smem);
@@ -1500,7 +1504,8 @@ cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, uint64_t first_id
     auto kern = ba_in_smem ? sigma_sort_kernel<false> : sigma_sort_kernel<true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
     if (e != cudaSuccess) return e;
-    kern<<<grid, kSigmaThreads, smem, st>>>(P, seed, first_id, n_tasks, B1, B2, pb, pairing_out, scratch, (uint32_t)list_cap);
+    kern<<<grid, kSigmaThreads, smem, st>>>(P, seed, seeds, seg ? seg : 1u, first_id, n_tasks, B1, B2, pb, pairing_out, scratch,
+                                            (uint32_t)list_cap);
     return cudaGetLastError();
 }
 

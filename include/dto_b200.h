@@ -123,6 +123,20 @@ int dto_b200_grid_debug(dto_b200_ctx *ctx, const uint32_t *perm1, const uint32_t
 int dto_b200_hypergeometric_pvalues(dto_b200_ctx *ctx, const uint64_t *N, const uint64_t *K, const uint64_t *n,
                                     const uint64_t *k, size_t count, double *pvalue_out);
 
+/* ---------------------------------------------------------------------------------------------------
+ * One process per GPU: the small all-gather of per-permutation minima over NVLink that replaces the MPI gather of
+ * src/run/multi_node.rs:148-160.  NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy the host application
+ * already mapped, else the system's); DTO_B200_ERR_UNSUPPORTED if there is none.  `nccl_comm` is an ncclComm_t with one
+ * rank per GPU: the caller's own, or one made with the two helpers below (unique id = 128 bytes, created on rank 0 and
+ * handed to the other ranks by whatever means the application has).
+ * allgather_minima: d_send = `count` doubles on ctx's device (e.g. d_minp_out of dto_b200_run_permuted_philox_device),
+ * d_recv = count x n_ranks doubles, rank-major.  Enqueued on the library's stream; synchronous on return.
+ * ------------------------------------------------------------------------------------------------- */
+int dto_b200_nccl_unique_id(void *id_out_128_bytes);
+int dto_b200_nccl_comm_create(void **comm_out, int n_ranks, const void *unique_id_128_bytes, int rank, int device);
+int dto_b200_nccl_comm_destroy(void *nccl_comm);
+int dto_b200_allgather_minima(dto_b200_ctx *ctx, void *nccl_comm, const double *d_send, double *d_recv, size_t count);
+
 typedef struct dto_b200_stats {
     uint64_t tasks_fast;        /* tasks solved by the warp-per-permutation scan kernel */
     uint64_t tasks_full;        /* re-run through the full-grid exact pipeline (min p >= 1 / no candidate) */
@@ -143,6 +157,9 @@ typedef struct dto_b200_stats {
     uint64_t tie_cells_host;     /* cells re-evaluated on the host for that */
 } dto_b200_stats;
 int dto_b200_get_stats(dto_b200_ctx *ctx, dto_b200_stats *out);
+/* process-wide totals since load, over every context including the pooled ones the host layer uses internally:
+ * out3 = {kernel launches of this library, bytes copied host->device, bytes copied device->host} */
+int dto_b200_process_totals(uint64_t *out3);
 int dto_b200_reset_stats(dto_b200_ctx *ctx);
 
 /* diagnostics: per-task {screened cells, recurrence-refined cells, exactly evaluated cells, then SM cycles / 16 of:
@@ -208,9 +225,19 @@ int dto_b200_optimize(dto_b200_ctx *ctx, const dto_b200_ranked_list *l1, const d
  * Task.permute (src/run/task.rs:3-9).  records_out[t] belongs to task t.  Work is sharded over the devices
  * listed (n_devices == 0 -> device 0 only); this replaces both the thread pool and the MPI scatter/gather of
  * src/run/multi_node.rs:114-161 on one box.  Permuted task t uses philox id t under `seed`. */
+/* Seeds: the null is a pure function of (seed, Philox id).  The CLI draws `seed` from the OS when --seed is absent (the
+ * reference shuffles with thread_rng, permuted.rs:58) and uses ids 1 .. permutations; dto_b200_run_pairs gives pair q the
+ * seed  seed + q * 0x9E3779B97F4A7C15  and the same ids, so pair 0 of a batch reproduces the CLI run with that --seed. */
 int dto_b200_run_single_node(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, uint64_t population,
                              const uint8_t *task_permute, size_t n_tasks, const int *devices, size_t n_devices,
                              uint64_t seed, dto_b200_record *records_out);
+
+/* The same with explicit Task.id values (src/run/task.rs:3-9): permuted task t uses Philox id task_ids[t] (NULL: id = t).
+ * Lets a caller that shards one job over several processes (one rank per GPU, as src/run/multi_node.rs:114-161 shards over
+ * MPI ranks) hand each process its id range and still obtain the results of the single-process run. */
+int dto_b200_run_tasks(const dto_b200_ranked_list *l1, const dto_b200_ranked_list *l2, uint64_t population,
+                       const uint64_t *task_ids, const uint8_t *task_permute, size_t n_tasks, const int *devices,
+                       size_t n_devices, uint64_t seed, dto_b200_record *records_out);
 
 /* fdr (src/stat_operations/fdr.rs:29-60); sensitivity <= 0 -> DTO_B200_ERR_PANIC */
 int dto_b200_fdr(uint64_t list1_len, uint64_t list2_len, uint64_t overlap, uint64_t population, double sensitivity,

@@ -716,3 +716,172 @@ def test_tie_sets_are_settled_like_the_reference(engine):
     want = float((ref["pvalue"] <= float(ob["pvalue"])).mean())
     assert dto.empirical_pvalue(all_recs)["empirical_pvalue"] == want
     assert float(un["pvalue"]) == float(ob["pvalue"]) and int(un["flags"]) & dto._capi.FLAG_HOST_PVALUE
+
+
+def _pair_reference(l1, l2, pop, P, seed):
+    """what dto_b200_run_pairs promises for one pair: the CLI run on [unpermuted, P permuted tasks with ids 1..P]"""
+    tasks = [dto.Task(0, False)] + [dto.Task(i, True) for i in range(1, P + 1)]
+    return dto.empirical_pvalue(dto.run.run_single_node_records(tasks, l1, l2, pop, 1, [0], seed))
+
+
+def test_pair_groups_equal_pair_by_pair_runs(engine):
+    """config 4 driver: consecutive pairs with one rank structure share a launch (their unpermuted tasks ride through
+    the scan kernel); a pair of another size, a tied pair and a pair with differing gene sets break the groups.  Every
+    result must equal the pair's own CLI-style run with seed + q * 0x9E37..., whatever the grouping."""
+    specs = [(400, 1, 0.3, 0.0), (400, 2, None, 0.0), (400, 3, 0.0, 0.0), (400, 4, 0.25, 0.0), (350, 5, 0.3, 0.0), (400, 6, None, 0.0),
+             (400, 7, 0.3, 0.2), (400, 8, None, 0.0), (400, 9, 0.35, 0.0)]
+    pairs = []
+    for n, s, sg, tied in specs:
+        ids1, r1, ids2, r2 = H.synthetic_pair(n, s, sg, tied_frac=tied)
+        if s % 2 == 0:  # different gene order in the two lists: the gene map really differs from pair to pair
+            order = np.random.default_rng(s).permutation(n)
+            ids2 = [ids2[i] for i in order]
+            r2 = r2[order]
+        l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+        pairs.append((l1, l2, dto.compute_population_size(l1, l2, None)))
+    ids1, r1, ids2, r2, bg = H.background_case(500, 380, 360, 11)
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    pairs.insert(4, (l1, l2, dto.compute_population_size(l1, l2, dto.FeatureList(bg))))
+    P, seed = 300, 99
+    got = dto.run_pairs(pairs, P, devices=[0], seed=seed)
+    for q, (l1, l2, pop) in enumerate(pairs):
+        want = _pair_reference(l1, l2, pop, P, (seed + q * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+        assert got[q] == want, (q, got[q], want)
+    # the unpermuted optimum of every pair against the oracle (p bit-exact: evaluated with the host libm)
+    for q, (n, s, sg, tied) in enumerate(specs[:4]):
+        ids1, r1, ids2, r2 = H.synthetic_pair(n, s, sg, tied_frac=tied)
+        if s % 2 == 0:
+            order = np.random.default_rng(s).permutation(n)
+            ids2 = [ids2[i] for i in order]
+            r2 = r2[order]
+        o1, o2 = H.oracle_lists(ids1, r1, ids2, r2)
+        ob = O.grid_int(o1, o2, n).best
+        assert (got[q]["rank1"], got[q]["rank2"], got[q]["unpermuted_intersection_size"]) == (int(ob["rank1"]), int(ob["rank2"]), int(ob["intersection_size"]))
+        assert got[q]["unpermuted_pvalue"] == float(ob["pvalue"])
+    # P = 0: only the unpermuted task, empirical p = 1.0 by definition (empirical_pvalue.rs:150-158)
+    z = dto.run_pairs(pairs[:3], 0, devices=[0], seed=seed)
+    assert all(r["empirical_pvalue"] == 1.0 for r in z) and [r["rank1"] for r in z] == [r["rank1"] for r in got[:3]]
+
+
+def test_run_tasks_with_ids_shards_like_the_unsharded_run(engine):
+    """Task.id is the Philox id (src/run/task.rs:3-9): two processes' worth of task slices reproduce the single run."""
+    ids1, r1, ids2, r2 = H.synthetic_pair(800, 12, 0.3)
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    tasks = [dto.Task(0, False)] + [dto.Task(i, True) for i in range(1, 501)]
+    whole = dto.run.run_single_node_records(tasks, l1, l2, 800, 1, [0], 5)
+    a = dto.run.run_single_node_records(tasks[:201], l1, l2, 800, 1, [0], 5)
+    b = dto.run.run_single_node_records(tasks[201:], l1, l2, 800, 1, [0], 5)
+    assert np.array_equal(np.concatenate([a, b]), whole)
+    # non-contiguous ids, unpermuted task in the middle
+    mixed = [tasks[7], tasks[3], tasks[0], tasks[500], tasks[499]]
+    m = dto.run.run_single_node_records(mixed, l1, l2, 800, 1, [0], 5)
+    assert np.array_equal(m, whole[[7, 3, 0, 500, 499]])
+
+
+def test_product_allgather_single_rank(engine):
+    """dto_b200_allgather_minima with a one-rank communicator made by the library's own helpers (the plumbing a host
+    application without torch uses); the multi-rank form is exercised by test_multi_gpu_* and bench.py under torchrun."""
+    import ctypes as C
+
+    import torch
+
+    capi = dto._capi
+    ids1, r1, ids2, r2 = H.synthetic_pair(600, 3, None)
+    load(engine, ids1, r1, ids2, r2)
+    uid = (C.c_char * 128)()
+    capi.check(capi.lib().dto_b200_nccl_unique_id(uid))
+    comm = C.c_void_p()
+    capi.check(capi.lib().dto_b200_nccl_comm_create(C.byref(comm), 1, uid, 0, 0))
+    P = 257
+    d_minp = torch.zeros(P, dtype=torch.float64, device="cuda:0")
+    d_all = torch.zeros(P, dtype=torch.float64, device="cuda:0")
+    engine.run_permuted_philox_device(3, 1, P, d_minp.data_ptr())
+    capi.check(capi.lib().dto_b200_allgather_minima(engine.ctx, comm, C.c_void_p(d_minp.data_ptr()), C.c_void_p(d_all.data_ptr()), P))
+    want = engine.run_permuted_philox(3, 1, P)["pvalue"]
+    assert np.array_equal(d_all.cpu().numpy(), want)
+    capi.check(capi.lib().dto_b200_nccl_comm_destroy(comm))
+
+
+def _n_gpus():
+    return dto.device_count()
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_multi_gpu_in_process_equals_one_gpu(engine):
+    """run_single_node(devices=[0, 1, ..]) -- what `-m` of the CLI maps to, replacing multi_node.rs:114-161 on one box --
+    returns the records of the one-GPU run; so does dto_b200_run_pairs sharded by pair."""
+    import json
+    import os
+    import subprocess
+
+    G = min(_n_gpus(), 8)
+    ids1, r1, ids2, r2 = H.synthetic_pair(3000, 21, 0.3)
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    tasks = [dto.Task(0, False)] + [dto.Task(i, True) for i in range(1, 4001)]
+    one = dto.run.run_single_node_records(tasks, l1, l2, 3000, 1, [0], 17)
+    many = dto.run.run_single_node_records(tasks, l1, l2, 3000, 1, list(range(G)), 17)
+    assert np.array_equal(one, many)
+    pairs = []
+    for q in range(2 * G + 1):
+        a, b, c, d = H.synthetic_pair(500, 100 + q, 0.3 if q % 2 else None)
+        x, y = dto.RankedFeatureList.from_(a, b), dto.RankedFeatureList.from_(c, d)
+        pairs.append((x, y, 500))
+    assert dto.run_pairs(pairs, 200, devices=[0], seed=3) == dto.run_pairs(pairs, 200, devices=list(range(G)), seed=3)
+    td = os.path.join(H.GOLDEN, "test_data")
+    base = [dto._capi.CLI_PATH, "-1", f"{td}/ranklist1.csv", "-2", f"{td}/ranklist2.csv", "-p", "3000", "--seed", "7"]
+    a = subprocess.run(base, capture_output=True, text=True, timeout=300)
+    b = subprocess.run(base + ["-m"], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0 and json.loads(a.stdout) == json.loads(b.stdout)
+
+
+def _allgather_worker(rank, world, uid_bytes, q):
+    import ctypes as C
+
+    import torch
+
+    capi = dto._capi
+    try:
+        ids1, r1, ids2, r2 = H.synthetic_pair(700, 4, None)
+        l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+        with dto.Engine(rank) as eng:
+            eng.load_lists(l1, l2, 700)
+            comm = C.c_void_p()
+            uid = (C.c_char * 128).from_buffer_copy(uid_bytes)
+            capi.check(capi.lib().dto_b200_nccl_comm_create(C.byref(comm), world, uid, rank, rank))
+            P = 300
+            torch.cuda.set_device(rank)
+            d_minp = torch.zeros(P, dtype=torch.float64, device=f"cuda:{rank}")
+            d_all = torch.zeros(P * world, dtype=torch.float64, device=f"cuda:{rank}")
+            eng.run_permuted_philox_device(9, 1 + rank * P, P, d_minp.data_ptr())
+            capi.check(capi.lib().dto_b200_allgather_minima(eng.ctx, comm, C.c_void_p(d_minp.data_ptr()), C.c_void_p(d_all.data_ptr()), P))
+            q.put((rank, d_all.cpu().numpy()))
+            capi.check(capi.lib().dto_b200_nccl_comm_destroy(comm))
+    except Exception as e:  # surface the failure to the parent instead of hanging it
+        q.put((rank, repr(e)))
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+def test_multi_gpu_product_allgather_over_nccl(engine):
+    """One process per GPU, raw ncclComm made with the library's helpers (no torch.distributed): every rank ends up with
+    the minima of all ranks, equal to the single-GPU run over the whole id range."""
+    import ctypes as C
+    import multiprocessing as mp
+
+    capi = dto._capi
+    world = 2
+    uid = (C.c_char * 128)()
+    capi.check(capi.lib().dto_b200_nccl_unique_id(uid))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allgather_worker, args=(r, world, bytes(uid.raw), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    ids1, r1, ids2, r2 = H.synthetic_pair(700, 4, None)
+    load(engine, ids1, r1, ids2, r2)
+    want = engine.run_permuted_philox(9, 1, 300 * world)["pvalue"]
+    for r in range(world):
+        assert isinstance(got[r], np.ndarray), got[r]
+        assert np.array_equal(got[r], want)
