@@ -40,7 +40,7 @@ struct Problem {
     int CH;          // columns per lane in the scan kernel (template value actually used)
     int CHP;         // hist_words(CH): 32-bit words per lane of the per-warp row histogram (two 16-bit column counts per
                      // word, padded to whole 16-byte vectors with an odd vector count so 128-bit reads are conflict-free)
-    int T2pad;       // 32 * CH
+    int T2pad;       // u16 entries per row of the critical-overlap tables: kcrit_row_u16(CH)
     int levels;      // number of screen levels beyond level 0
     uint32_t never;  // kcrit value meaning "no overlap passes": 0x7FFF when every set size is <= 32766 (packed 15-bit
                      // screen), else 0xFFFF
@@ -111,11 +111,15 @@ __host__ __device__ inline uint32_t hist_slot_column(uint32_t slot, int CH) {
     return (word / W) * (uint32_t)CH + 2u * (word % W) + (slot & 1u);
 }
 
-// Position of column j inside a kcrit row: lane = j / CH owns columns m = j % CH; its pair m/2 is one 32-bit word and
-// the words of pair q are contiguous across lanes, so a warp reads a row with CH/2 coalesced 128-byte loads.
+// Position of column j inside a kcrit row (u16 units): lane = j / CH owns columns m = j % CH; its pair q = m / 2 is one
+// 32-bit word; the lane's pairs 4v .. 4v+3 form one 16-byte vector, and vector v of all 32 lanes is contiguous, so a warp
+// reads a row with ceil(CH/8) perfectly coalesced 128-bit loads (512 contiguous bytes each).  Words of pairs >= CH/2 are
+// padding and hold "never".
+__host__ __device__ constexpr int kcrit_vecs(int CH) { return (CH / 2 + 3) / 4; }
+__host__ __device__ constexpr int kcrit_row_u16(int CH) { return kcrit_vecs(CH) * 32 * 4 * 2; }
 __host__ __device__ inline size_t kcrit_col(int j, int CH) {
-    const int lane = j / CH, m = j % CH;
-    return ((size_t)(m >> 1) * 32 + (size_t)lane) * 2 + (size_t)(m & 1);
+    const int lane = j / CH, m = j % CH, q = m >> 1;
+    return (((size_t)(q >> 2) * 32 + (size_t)lane) * 4 + (size_t)(q & 3)) * 2 + (size_t)(m & 1);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -692,7 +692,7 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     P.T2 = (int)T2;
     P.CH = pick_ch((int)T2);
     P.CHP = hist_words(P.CH);
-    P.T2pad = 32 * P.CH;
+    P.T2pad = kcrit_row_u16(P.CH);
     P.levels = ctx->opt_levels;
     P.n1 = (uint32_t)n1;
     P.n2 = (uint32_t)n2;

@@ -56,7 +56,7 @@ std::atomic<uint64_t> g_next_list_uid{1};
 // reuse warm buffers.  Contexts are never shared between threads while in use; idle ones are kept until process exit.
 std::mutex g_pool_mu;
 std::vector<dto_b200_ctx *> g_pool[64];
-constexpr size_t kPoolPerDevice = 8;
+constexpr size_t kPoolPerDevice = 4;
 
 int pool_acquire(dto_b200_ctx **ctx_out, int device) {
     {
@@ -73,7 +73,9 @@ int pool_acquire(dto_b200_ctx **ctx_out, int device) {
 void pool_release(dto_b200_ctx *ctx, int device, bool healthy) {
     if (!ctx) return;
     if (healthy && device >= 0 && device < 64) {
-        dto::trim_batch_buffers(ctx, (size_t)256 << 20);
+        // an idle context keeps its batch buffers up to 6 GiB each (one 100 000-permutation batch of partner-slot rows at
+        // N = 20 000 is 4 GB; re-allocating it on every call costs milliseconds), the pool holds at most kPoolPerDevice
+        dto::trim_batch_buffers(ctx, (size_t)6 << 30);
         std::lock_guard<std::mutex> lock(g_pool_mu);
         if (g_pool[device].size() < kPoolPerDevice) {
             g_pool[device].push_back(ctx);

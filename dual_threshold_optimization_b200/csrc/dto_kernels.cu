@@ -324,6 +324,87 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
     __syncthreads();
 }
 
+// ---- explicit shared-space accesses for the hot loops of the row-wise variant: the pointers of SortShared are generic
+// ---- (they may also point into the global scratch), and a generic atomic / load costs an address-space conversion each
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t atoms_inc(uint32_t addr) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(addr) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+
+// bucket counters (and the boundary-list counter) back to zero, 128 bits per store
+__device__ __forceinline__ void block_zero_counters_fast(const SortShared &S, int B) {
+    const uint32_t NB = 1u << B;
+    if (NB >= 4) {
+        const uint32_t base = smem_addr(S.cnt);
+        for (uint32_t x = threadIdx.x; x < NB / 4; x += blockDim.x) sts128(base + x * 16, 0u, 0u, 0u, 0u);
+        if (threadIdx.x == 0) S.cnt[NB] = 0;
+    } else {
+        for (uint32_t x = threadIdx.x; x <= NB; x += blockDim.x) S.cnt[x] = 0;
+    }
+    if (threadIdx.x == 0) S.scan_tmp[32] = 0;
+}
+
+// Pass 1 of the row-wise variant (S.ba in shared memory): same result as block_bucket_keys, branch-free per element.
+// Blocks of 8 elements that lie entirely below n take the lean path; the one partial block (n % 8 != 0) is checked.
+__device__ __forceinline__ void block_bucket_keys_lean(const SortShared &S, uint32_t n, int B, uint64_t seed,
+                                                       uint64_t perm_id, uint32_t stream) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t n8 = (n + 7) >> 3, full = n >> 3;
+    const uint32_t cnt_a = smem_addr(S.cnt), ba_a = smem_addr(S.ba);
+    const uint32_t sh = 32u - (uint32_t)B;  // bucket of the key in the HIGH half of a Philox word: w >> sh
+    for (uint32_t c = tid; c < full; c += nt) {
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+        uint32_t v[8];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const uint32_t w = key[h];  // low half = element 8c + 2h, high half = element 8c + 2h + 1
+            const uint32_t wl = w << 16;
+            const uint32_t a0 = atoms_inc(cnt_a + ((wl >> sh) << 2));
+            const uint32_t a1 = atoms_inc(cnt_a + ((w >> sh) << 2));
+            v[2 * h] = wl | a0;
+            v[2 * h + 1] = (w & 0xFFFF0000u) | a1;
+        }
+        sts128(ba_a + c * 16, v[0], v[1], v[2], v[3]);
+        sts128(ba_a + (n8 + c) * 16, v[4], v[5], v[6], v[7]);
+    }
+    if (full < n8 && tid == (full % nt)) {  // the partial block
+        const uint32_t c = full;
+        uint32_t key[4];
+        philox_keys(key, seed, perm_id, stream, c);
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t e = c * 8 + q;
+            const uint32_t k16 = (q & 1) ? (key[q >> 1] >> 16) : (key[q >> 1] & 0xFFFFu);
+            v[q] = k16 << 16;
+            if (e < n) v[q] |= atoms_inc(cnt_a + ((k16 >> (16 - B)) << 2));
+        }
+        sts128(ba_a + c * 16, v[0], v[1], v[2], v[3]);
+        sts128(ba_a + (n8 + c) * 16, v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    block_exclusive_scan(S.cnt, 1u << B, S.scan_tmp);
+}
+
 // Row-wise variant, used when only the ROW of every list-1 position matters (identical gene sets, no export): positions
 // inside one threshold row are interchangeable for the overlap grid, so an element whose whole bucket lies inside one
 // row takes position off[bucket] + arrival without being ranked.  Buckets that contain a row boundary strictly inside
@@ -331,13 +412,22 @@ __device__ void block_rank_by_random_keys(const SortShared &S, uint32_t n, int B
 // only their elements (~5-8 %) get a secondary key and an exact rank, entirely in shared memory: the staged row itself
 // holds the member list of such a bucket until the ranks are known.  The result is the exact variant's permutation up
 // to within-row order; the records it leads to are identical.
+//
+// The placement loop touches every element and is therefore kept minimal (per element: bucket offset, position, one
+// select, one 16-bit store); everything about boundary buckets happens on the side: the thread that owns the FIRST
+// boundary inside such a bucket lists its members afterwards (they sit in the staged row), and the ~6 % of elements on
+// that list are then ranked by all threads.
+template <bool BA_SHARED>
 __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const uint32_t *bounds, uint32_t n, int B,
                                     uint64_t seed, uint64_t perm_id, uint32_t stream, uint16_t *stage) {
-    block_bucket_keys(S, n, B, seed, perm_id, stream, true);  // the kernel zeroes the counters during the copy-out
+    if constexpr (BA_SHARED) block_bucket_keys_lean(S, n, B, seed, perm_id, stream);
+    else block_bucket_keys(S, n, B, seed, perm_id, stream, true);  // the kernel zeroes the counters during the copy-out
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    // flag the buckets a row boundary p cuts (off[b] < p < off[b+1]); T1 <= 2048 = 2 boundaries per thread
-    uint32_t cut[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    const uint32_t lane = tid & 31u;
+    // the bucket a row boundary p cuts (off[b] < p < off[b+1]), per boundary; T1 <= 2048 = 2 boundaries per thread.
+    // own[r] = that bucket if this boundary is the FIRST one inside it (the previous boundary lies at or before its start)
+    uint32_t own[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const uint32_t x = tid + (uint32_t)r * nt;
@@ -350,16 +440,67 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
                     if (S.cnt[mid] <= p) lo = mid;
                     else hi = mid;
                 }
-                if (S.cnt[lo] < p) cut[r] = lo;
+                const uint32_t start = S.cnt[lo];
+                if (start < p && (x == 0 || bounds[x - 1] <= start)) own[r] = lo;
             }
         }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 2; ++r)
-        if (cut[r] != 0xFFFFFFFFu) atomicOr(&S.cnt[cut[r]], 0x80000000u);
+        if (own[r] != 0xFFFFFFFFu) S.cnt[own[r]] |= 0x80000000u;  // one owner per bucket: a plain store
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
+    const uint32_t steps = 2 * n8;
+    if constexpr (BA_SHARED) {
+        // placement, 4 elements (one 128-bit word of ba, one 8-byte word of partner slots) per step.  An element of a
+        // boundary bucket stores its own index (the staged row doubles as the member list of such a bucket; it holds
+        // >= n entries), any other element its partner slot.  Positions past the last threshold are overwritten with
+        // kNoSlot after the ranking.  Only the two steps of the partial key block (n % 8 != 0) check e < n.
+        const uint32_t cnt_a = smem_addr(S.cnt), ba_a = smem_addr(S.ba), st_a = smem_addr(stage);
+        const uint32_t sh = 32u - (uint32_t)B;
+        const bool tail = (n & 7u) != 0u;
+        for (uint32_t u = tid; u < steps; u += nt) {
+            const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
+            const uint4 va = lds128(ba_a + u * 16);
+            const uint2 dsv = __ldg(reinterpret_cast<const uint2 *>(P.dslot2 + e0));  // dslot2 is padded to a multiple of 8
+            const uint32_t v[4] = {va.x, va.y, va.z, va.w};
+            const uint32_t ds[4] = {dsv.x & 0xFFFFu, dsv.x >> 16, dsv.y & 0xFFFFu, dsv.y >> 16};
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = lds32(cnt_a + ((v[q] >> sh) << 2));
+            if (!tail || (u != n8 - 1 && u != steps - 1)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t pos = (w[q] & kPosMask) + (v[q] & 0xFFFFu);
+                    sts16(st_a + 2 * pos, (int32_t)w[q] < 0 ? e0 + q : ds[q]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t pos = (w[q] & kPosMask) + (v[q] & 0xFFFFu);
+                    if (e0 + q < n) sts16(st_a + 2 * pos, (int32_t)w[q] < 0 ? e0 + q : ds[q]);
+                }
+            }
+        }
+    } else {
+        const uint4 *ba4 = reinterpret_cast<const uint4 *>(S.ba);
+        for (uint32_t u = tid; u < steps; u += nt) {
+            const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
+            const uint4 va = ba4[u];
+            const uint32_t v[4] = {va.x, va.y, va.z, va.w};
+            const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + e0);
+            const uint32_t ds[4] = {dsv.x & 0xFFFFu, dsv.x >> 16, dsv.y & 0xFFFFu, dsv.y >> 16};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t e = e0 + q;
+                const uint32_t w = S.cnt[v[q] >> (32 - B)];
+                const uint32_t pos = (w & kPosMask) + (v[q] & 0xFFFFu);
+                if (e < n) stage[pos] = (uint16_t)((w >> 31) ? e : ds[q]);
+            }
+        }
+    }
+    __syncthreads();
     // the boundary list: first list_cap entries in shared memory, the rest in the global scratch (two explicit branches
     // so that each side is a plain shared / global access, not a generic one)
     auto lst_put = [&](uint32_t x, uint32_t v) {
@@ -367,48 +508,27 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         else S.list_g[x] = v;
     };
     auto lst_get = [&](uint32_t x) -> uint32_t { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
-    // placement, 4 elements (one 128-bit word of ba, one 8-byte word of partner slots) per step, branch-free: an element
-    // of a boundary bucket stores its own index (the staged row doubles as the member list of such a bucket; it holds
-    // >= n entries), any other element its partner slot.  The boundary elements of a warp's step are appended to the
-    // list with one warp-aggregated atomic.
-    const uint4 *ba4 = reinterpret_cast<const uint4 *>(S.ba);
-    const uint32_t lane = tid & 31u;
-    const uint32_t steps = 2 * n8, steps_warp = (steps + 31u) & ~31u;  // whole warps stay in the loop (votes, shuffles)
-    for (uint32_t u = tid; u < steps_warp; u += nt) {
-        uint32_t cutmask = 0, ent[4] = {0u, 0u, 0u, 0u};
-        if (u < steps) {
-            const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
-            const uint4 va = ba4[u];
-            const uint32_t v[4] = {va.x, va.y, va.z, va.w};
-            const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + e0);  // dslot2 is padded to a multiple of 8
-            const uint32_t ds[4] = {dsv.x & 0xFFFFu, dsv.x >> 16, dsv.y & 0xFFFFu, dsv.y >> 16};
+    // owners append (bucket << 16 | element) for every member of their bucket: one warp-aggregated reservation per warp
+    // that owns anything (T1 boundaries: the first T1 threads, plus a second round when T1 > blockDim)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t e = e0 + q;
-                const uint32_t b = v[q] >> (32 - B);
-                const uint32_t w = S.cnt[b];
-                const uint32_t pos = (w & kPosMask) + (v[q] & 0xFFFFu);
-                const bool cutb = (w >> 31) != 0u;
-                if (e < n && (cutb || pos < P.n1_eff)) stage[pos] = (uint16_t)(cutb ? e : ds[q]);
-                ent[q] = (b << 16) | e;
-                if (e < n && cutb) cutmask |= 1u << q;
-            }
+    for (int r = 0; r < 2; ++r) {
+        if ((uint32_t)r * nt >= (uint32_t)P.T1) break;          // block-uniform
+        if ((tid & ~31u) + (uint32_t)r * nt >= (uint32_t)P.T1) continue;  // warp-uniform: no boundary in this warp
+        uint32_t lo = 0, m = 0;
+        if (own[r] != 0xFFFFFFFFu) {
+            lo = S.cnt[own[r]] & kPosMask;
+            m = (S.cnt[own[r] + 1] & kPosMask) - lo;
         }
-        if (__any_sync(kFull, cutmask != 0u)) {
-            const uint32_t nf = __popc(cutmask);
-            uint32_t inc = nf;
+        uint32_t inc = m;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, inc, o);
-                if (lane >= (uint32_t)o) inc += t;
-            }
-            uint32_t base = 0;
-            if (lane == 31) base = atomicAdd(&S.scan_tmp[32], inc);
-            base = __shfl_sync(kFull, base, 31) + inc - nf;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (cutmask & (1u << q)) lst_put(base + __popc(cutmask & ((1u << q) - 1u)), ent[q]);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
         }
+        uint32_t base = 0;
+        if (lane == 31 && inc) base = atomicAdd(&S.scan_tmp[32], inc);
+        base = __shfl_sync(kFull, base, 31) + inc - m;
+        for (uint32_t y = 0; y < m; ++y) lst_put(base + y, (own[r] << 16) | (uint32_t)stage[lo + y]);
     }
     __syncthreads();
     const uint32_t n_list = S.scan_tmp[32];
@@ -434,11 +554,10 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     __syncthreads();
     for (uint32_t x = tid; x < n_list; x += nt) {
         const uint32_t ent = lst_get(x);
-        const uint32_t f = ent >> 16;
-        if (f < P.n1_eff) stage[f] = P.dslot2[ent & 0xFFFFu];
+        stage[ent >> 16] = P.dslot2[ent & 0xFFFFu];
     }
-    // positions past the last threshold carry no partner (disjoint from the writes above; member lists that reached into
-    // this range were consumed before the previous barrier)
+    __syncthreads();
+    // positions past the last threshold carry no partner
     for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
     __syncthreads();
 }
@@ -486,7 +605,7 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     const bool rowwise = identical && pairing_out == nullptr;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     if (rowwise) {
-        block_zero_counters(S, B2);
+        block_zero_counters_fast(S, B2);
         __syncthreads();
     }
 
@@ -496,7 +615,7 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
         const uint64_t perm_id = first_id + (uint64_t)(seeds ? (uint32_t)t % seg : (uint32_t)t);
         uint16_t *dst = pb + (size_t)t * P.pb_stride;
         if (rowwise) {
-            block_place_rowwise(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
+            block_place_rowwise<!BA_IN_SCRATCH>(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
         } else if (identical) {
             // element = list-2 position e, rank f = the list-1 position it is paired with
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
@@ -520,12 +639,12 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
             for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
             __syncthreads();
         }
-        // coalesced copy-out, 8 bytes per thread (pb_stride is a multiple of 256, rows are 512 B aligned); the row-wise
+        // coalesced copy-out, 16 bytes per thread (pb_stride is a multiple of 256, rows are 512 B aligned); the row-wise
         // variant clears its bucket counters for the next permutation in the same phase
-        const uint2 *s2 = reinterpret_cast<const uint2 *>(stage);
-        uint2 *d2 = reinterpret_cast<uint2 *>(dst);
-        for (uint32_t x = tid; x < P.pb_stride / 4; x += nt) d2[x] = s2[x];
-        if (rowwise) block_zero_counters(S, B2);
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (uint32_t x = tid; x < P.pb_stride / 8; x += nt) d4[x] = s4[x];
+        if (rowwise) block_zero_counters_fast(S, B2);
         __syncthreads();
     }
 }
@@ -989,8 +1108,6 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
 // scan_rows, in registers inside it).
 template <int CH>
 struct RowState {
-    uint32_t kcur2[CH / 2];  // overlap counts of this lane's CH columns, two 16-bit counts per word (k <= 65534)
-    uint32_t koff2;          // overlap contributed by the lanes to the left, in both halves
     uint32_t qn;             // warp-uniform copy of the queue length (refreshed only after rows that pushed something)
     uint32_t lo, cbase;      // next list-1 position; oldest resident chunk of the partner-slot ring
     int i, level;            // next row; screen level
@@ -1023,10 +1140,7 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
     const uint16_t *ring = reinterpret_cast<const uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t n_chunks = P.pb_stride / kChunk;
-    uint32_t kcur2[NP];
-#pragma unroll
-    for (int q = 0; q < NP; ++q) kcur2[q] = st.kcur2[q];
-    uint32_t koff2 = st.koff2, qn = st.qn, lo = st.lo, cbase = st.cbase;
+    uint32_t qn = st.qn, lo = st.lo, cbase = st.cbase;
     int i = st.i;
     const int level = st.level;
     auto advance_ring = [&]() {  // chunk cbase is consumed: cbase+2 must have landed, refill the freed slot
@@ -1036,9 +1150,10 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
         ring_issue_chunk(row, n_chunks, ring_addr, lane, cbase + 2);
     };
     // this lane's words of the current row of critical overlaps (level `level`, row i), advanced row by row
-    const uint32_t *__restrict__ kr =
-        reinterpret_cast<const uint32_t *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
-    const uint32_t kr_step = (uint32_t)P.T2pad >> 1;  // 32-bit words per row
+    const uint4 *__restrict__ kr =
+        reinterpret_cast<const uint4 *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
+    const uint32_t kr_step = (uint32_t)P.T2pad >> 3;  // 16-byte vectors per row
+    constexpr int KV = kcrit_vecs(CH);
     const int T1 = P.T1;  // P lives behind a generic pointer here: read the loop bound once, not once per row
     uint4 *D4 = reinterpret_cast<uint4 *>(D + lane * CHP);  // this lane's column pairs, 4 per 128-bit vector
     {
@@ -1046,9 +1161,12 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
             const uint32_t hi = s_c1[i];
             // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
             // the scatter)
-            uint32_t kc2[NP];
+            uint32_t kc2[KV * 4];
 #pragma unroll
-            for (int q = 0; q < NP; ++q) kc2[q] = __ldg(kr + q * 32);
+            for (int v = 0; v < KV; ++v) {
+                const uint4 t = __ldg(kr + v * 32);
+                kc2[4 * v] = t.x, kc2[4 * v + 1] = t.y, kc2[4 * v + 2] = t.z, kc2[4 * v + 3] = t.w;
+            }
             kr += kr_step;
             // (1) bin this row's genes: position -> partner's column slot, privatised per warp.  Positions below
             // (cbase + 2) * kChunk are resident in the ring.
@@ -1068,28 +1186,31 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
                 advance_ring();
             }
             __syncwarp();
-            // (2) 2-D inclusive prefix, everything packed (two 16-bit counts per word; no field ever exceeds 65534):
-            // d = (x, y) of a column pair -> d * 0x10001 = (x, x + y); the running total rides in both halves.  Two
-            // independent half-length chains, the second one offset by the first one's total afterwards.
+            // (2) 2-D inclusive prefix, everything packed (two 16-bit counts per word; no field ever exceeds 65534).  The
+            // histogram is CUMULATIVE over the rows -- it is never cleared inside a permutation -- so word (x, y) of a column
+            // pair already holds the column totals of all rows so far and the prefix over the columns is the overlap k(i, .)
+            // itself: no per-row zeroing stores, no accumulators carried from row to row.  d = (x, y) of a column pair ->
+            // d * 0x10001 = (x, x + y); the running total rides in both halves.  Two independent half-length chains, the
+            // second one offset by the first one's total afterwards.
             constexpr int NV = (NP + 3) / 4, HA = NP / 2;
             uint32_t d[NV * 4];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 const uint4 t = D4[v];
-                D4[v] = make_uint4(0u, 0u, 0u, 0u);
                 d[4 * v] = t.x, d[4 * v + 1] = t.y, d[4 * v + 2] = t.z, d[4 * v + 3] = t.w;
             }
+            uint32_t kcur2[NP];  // overlap of this lane's columns in this row, without the lanes to the left
             uint32_t runA = 0, runB = 0;
 #pragma unroll
             for (int q = 0; q < HA; ++q) {
                 const uint32_t t = d[q] * 0x10001u + runA;
-                kcur2[q] += t;
+                kcur2[q] = t;
                 runA = __byte_perm(t, 0u, 0x3232);
             }
 #pragma unroll
             for (int q = HA; q < NP; ++q) {
                 const uint32_t t = d[q] * 0x10001u + runB;
-                kcur2[q] += t + runA;
+                kcur2[q] = t + runA;
                 runB = __byte_perm(t, 0u, 0x3232);
             }
             const uint32_t run2 = runA + runB;  // lane total in both halves
@@ -1099,7 +1220,7 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
                 const uint32_t v = __shfl_up_sync(kFull, inc2, o);
                 if (lane >= o) inc2 += v;
             }
-            koff2 += inc2 - run2;
+            const uint32_t koff2 = inc2 - run2;  // overlap contributed by the lanes to the left, in both halves
             // (3) screen: only k >= kcrit can have p <= tau_level
             auto screen = [&](int q) {
                 const uint32_t kk = kcur2[q] + koff2;  // no carry between the halves: every k < 65536
@@ -1157,9 +1278,6 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
             }
         }
     }
-#pragma unroll
-    for (int q = 0; q < NP; ++q) st.kcur2[q] = kcur2[q];
-    st.koff2 = koff2;
     st.qn = qn;
     st.lo = lo;
     st.cbase = cbase;
@@ -1218,9 +1336,7 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         R.lane = lane;
 
         RowState<CH> st;
-#pragma unroll
-        for (int q = 0; q < CH / 2; ++q) st.kcur2[q] = 0;
-        st.koff2 = st.qn = st.lo = st.cbase = 0;
+        st.qn = st.lo = st.cbase = 0;
         st.i = st.level = 0;
         // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
         // lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)

@@ -102,8 +102,33 @@ def to_json(rep, tasks, out_path):
     json.dump(d, open(out_path, "w"), indent=1)
 
 
+def counters(cfg, tag, tasks):
+    """profiles/kernel_counters_<cfg>.json (+ text summaries) from gpurun_out/<tag>_{scan,sigma}_<cfg>.ncu-rep."""
+    import contextlib
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    go = os.path.join(root, "gpurun_out")
+    sha = open(os.path.join(go, f"{tag}_{cfg}_sha.txt")).read().strip()
+    out = {"kernel_source_sha": sha,
+           "capture": {"tool": "ncu --set full --clock-control none --import-source on, one launch per kernel (4th launch: after 3 warm-up steps)",
+                       "command": f"bash tools/ncu_capture.sh {cfg} {tag} {tasks}", "permutations_in_launch": tasks, "tag": tag}}
+    for k in ("scan", "sigma"):
+        rep = os.path.join(go, f"{tag}_{k}_{cfg}.ncu-rep")
+        tmp = os.path.join(go, f"{tag}_{k}_{cfg}.json")
+        to_json(rep, tasks, tmp)
+        out[k] = json.load(open(tmp))
+        with open(os.path.join(root, "profiles", f"{tag}_{k}_kernel_ncu_{cfg}.txt"), "w") as f, contextlib.redirect_stdout(f):
+            main(rep, tasks)
+    json.dump(out, open(os.path.join(root, "profiles", f"kernel_counters_{cfg}.json"), "w"), indent=1)
+    print(json.dumps({k: {x: out[k][x] for x in ("warp_instructions_per_permutation", "issue_active_pct", "dram_bytes_per_permutation")} for k in ("scan", "sigma")}, indent=1))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 3:
+    if sys.argv[1] == "counters":
+        counters(sys.argv[2], sys.argv[3], int(sys.argv[4]))
+    elif len(sys.argv) > 3:
         to_json(sys.argv[1], int(sys.argv[2]), sys.argv[3])
     else:
         main(sys.argv[1], int(sys.argv[2]))
