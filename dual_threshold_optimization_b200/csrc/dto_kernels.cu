@@ -144,7 +144,7 @@ struct SortShared {
                          //         straddles a row boundary"
     uint32_t *ba;        // [8 * ceil(n/8)] (key16 << 16) | arrival slot inside the bucket, at ba_index(e); the row-wise
                          //         variant later replaces the entries of boundary-bucket elements by their tie-break word
-    uint32_t *scan_tmp;  // [33]: [0..31] warp partials of the block scan, [32] = boundary-list counter
+    uint32_t *scan_tmp;  // [kScanTmp]: warp partials of the block scan (4 slices x 32), [kListCtr] = boundary-list counter
     uint32_t *list_s;    // [list_cap] (shared) boundary-bucket elements: bucket << 16 | element, later position << 16 | element
     uint32_t *list_g;    // [n] (global scratch) the same list beyond list_cap entries
     uint32_t list_cap;
@@ -153,6 +153,7 @@ struct SortShared {
 };
 
 constexpr uint32_t kPosMask = 0x7FFFFFFFu;
+constexpr int kListCtr = 128, kScanTmp = 129;
 
 __device__ __forceinline__ void philox_keys(uint32_t (&out)[4], uint64_t seed, uint64_t perm_id, uint32_t stream,
                                             uint32_t block) {
@@ -241,11 +242,75 @@ __device__ void block_exclusive_scan_t(uint32_t *a, uint32_t len, uint32_t *tmp)
     __syncthreads();
 }
 
+// The same scan for len == 4 * V * blockDim.x with a bank-conflict-free access pattern: thread t owns the 128-bit vectors
+// t, t + nt, .., t + (V-1) nt (consecutive threads touch consecutive vectors), i.e. V slices of 4 nt counters each, scanned
+// as V simultaneous block scans whose totals chain from slice to slice.  (Contiguous ownership, 16 V bytes per thread,
+// makes every 128-bit access a 4-way conflict at V = 4: a quarter of all shared-memory wavefronts of the pairing kernel.)
+// tmp: V * 32 + 1 words.
+template <int V>
+__device__ void block_exclusive_scan_sliced(uint32_t *a, uint32_t *tmp) {
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+    uint4 *a4 = reinterpret_cast<uint4 *>(a);
+    uint4 r[V];
+    uint32_t sum[V], inc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        r[q] = a4[(uint32_t)q * nt + tid];
+        sum[q] = r[q].x + r[q].y + r[q].z + r[q].w;
+        inc[q] = sum[q];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            const uint32_t v = __shfl_up_sync(kFull, inc[q], o);
+            if (lane >= (uint32_t)o) inc[q] += v;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) tmp[q * 32 + w] = inc[q];
+    }
+    __syncthreads();
+    // every warp scans the V x nw warp totals itself (slice-major order): lane l holds warp l's total of every slice
+    uint32_t wv[V], ws[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        wv[q] = lane < nw ? tmp[q * 32 + lane] : 0u;
+        ws[q] = wv[q];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            const uint32_t u = __shfl_up_sync(kFull, ws[q], o);
+            if (lane >= (uint32_t)o) ws[q] += u;
+        }
+    }
+    uint32_t slice_base = 0;
+#pragma unroll
+    for (int q = 0; q < V; ++q) {
+        const uint32_t woff = __shfl_sync(kFull, ws[q] - wv[q], (int)w);  // exclusive offset of this warp inside slice q
+        const uint32_t tot = __shfl_sync(kFull, ws[q], 31);
+        uint32_t run = slice_base + woff + inc[q] - sum[q];
+        uint4 o4;
+        o4.x = run;
+        o4.y = o4.x + r[q].x;
+        o4.z = o4.y + r[q].y;
+        o4.w = o4.z + r[q].z;
+        a4[(uint32_t)q * nt + tid] = o4;
+        slice_base += tot;
+    }
+    if (tid == 0) a[4u * V * nt] = slice_base;  // total
+    __syncthreads();
+}
+
 __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     const uint32_t nt = blockDim.x;
-    if (len == 16 * nt) block_exclusive_scan_t<4>(a, len, tmp);
-    else if (len == 8 * nt) block_exclusive_scan_t<2>(a, len, tmp);
-    else if (len == 4 * nt) block_exclusive_scan_t<1>(a, len, tmp);
+    if (len == 16 * nt) block_exclusive_scan_sliced<4>(a, tmp);
+    else if (len == 8 * nt) block_exclusive_scan_sliced<2>(a, tmp);
+    else if (len == 4 * nt) block_exclusive_scan_sliced<1>(a, tmp);
     else block_exclusive_scan_t<0>(a, len, tmp);
 }
 
@@ -253,7 +318,7 @@ __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
 // (key16 << 16 | arrival) of every element.
 __device__ __forceinline__ void block_zero_counters(const SortShared &S, int B) {
     for (uint32_t x = threadIdx.x; x <= (1u << B); x += blockDim.x) S.cnt[x] = 0;
-    if (threadIdx.x == 0) S.scan_tmp[32] = 0;
+    if (threadIdx.x == 0) S.scan_tmp[kListCtr] = 0;
 }
 
 // pre_zeroed: the caller cleared the counters in an earlier phase that a barrier already closed
@@ -359,7 +424,7 @@ __device__ __forceinline__ void block_zero_counters_fast(const SortShared &S, in
     } else {
         for (uint32_t x = threadIdx.x; x <= NB; x += blockDim.x) S.cnt[x] = 0;
     }
-    if (threadIdx.x == 0) S.scan_tmp[32] = 0;
+    if (threadIdx.x == 0) S.scan_tmp[kListCtr] = 0;
 }
 
 // Pass 1 of the row-wise variant (S.ba in shared memory): same result as block_bucket_keys, branch-free per element.
@@ -425,30 +490,52 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t lane = tid & 31u;
-    // the bucket a row boundary p cuts (off[b] < p < off[b+1]), per boundary; T1 <= 2048 = 2 boundaries per thread.
-    // own[r] = that bucket if this boundary is the FIRST one inside it (the previous boundary lies at or before its start)
-    uint32_t own[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    // the boundary list: first list_cap entries in shared memory, the rest in the global scratch (two explicit branches
+    // so that each side is a plain shared / global access, not a generic one)
+    auto lst_put = [&](uint32_t x, uint32_t v) {
+        if (x < S.list_cap) S.list_s[x] = v;
+        else S.list_g[x] = v;
+    };
+    auto lst_get = [&](uint32_t x) -> uint32_t { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
+    // The bucket a row boundary p cuts (off[b] < p < off[b+1]), per boundary; T1 <= 2048 = 2 boundaries per thread.  The
+    // thread whose boundary is the FIRST one inside a bucket (the previous boundary lies at or before its start) owns it:
+    // it flags the bucket (bit 31 of its offset; one owner per bucket, so a plain store -- concurrent searches mask the
+    // bit out) and reserves one list entry per member, (bucket << 16 | member index); the member's element id is only
+    // known after the placement, which leaves it in the staged row.
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
+        if ((uint32_t)r * nt >= (uint32_t)P.T1) break;                    // block-uniform
+        if ((tid & ~31u) + (uint32_t)r * nt >= (uint32_t)P.T1) continue;  // warp-uniform: no boundary in this warp
         const uint32_t x = tid + (uint32_t)r * nt;
+        uint32_t own = 0xFFFFFFFFu, m = 0;
         if (x < (uint32_t)P.T1) {
             const uint32_t p = bounds[x];
             if (p > 0 && p < n) {
                 uint32_t lo = 0, hi = NB;  // largest b with off[b] <= p: the (non-empty) bucket holding position p
                 while (hi - lo > 1) {
                     const uint32_t mid = (lo + hi) >> 1;
-                    if (S.cnt[mid] <= p) lo = mid;
+                    if ((S.cnt[mid] & kPosMask) <= p) lo = mid;
                     else hi = mid;
                 }
-                const uint32_t start = S.cnt[lo];
-                if (start < p && (x == 0 || bounds[x - 1] <= start)) own[r] = lo;
+                const uint32_t start = S.cnt[lo] & kPosMask;
+                if (start < p && (x == 0 || bounds[x - 1] <= start)) {
+                    own = lo;
+                    m = (S.cnt[lo + 1] & kPosMask) - start;
+                    S.cnt[lo] = start | 0x80000000u;
+                }
             }
         }
-    }
-    __syncthreads();
+        uint32_t inc = m;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-        if (own[r] != 0xFFFFFFFFu) S.cnt[own[r]] |= 0x80000000u;  // one owner per bucket: a plain store
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        uint32_t base = 0;
+        if (lane == 31 && inc) base = atomicAdd(&S.scan_tmp[kListCtr], inc);
+        base = __shfl_sync(kFull, base, 31) + inc - m;
+        for (uint32_t y = 0; y < m; ++y) lst_put(base + y, (own << 16) | y);
+    }
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
     const uint32_t steps = 2 * n8;
@@ -501,41 +588,14 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         }
     }
     __syncthreads();
-    // the boundary list: first list_cap entries in shared memory, the rest in the global scratch (two explicit branches
-    // so that each side is a plain shared / global access, not a generic one)
-    auto lst_put = [&](uint32_t x, uint32_t v) {
-        if (x < S.list_cap) S.list_s[x] = v;
-        else S.list_g[x] = v;
-    };
-    auto lst_get = [&](uint32_t x) -> uint32_t { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
-    // owners append (bucket << 16 | element) for every member of their bucket: one warp-aggregated reservation per warp
-    // that owns anything (T1 boundaries: the first T1 threads, plus a second round when T1 > blockDim)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        if ((uint32_t)r * nt >= (uint32_t)P.T1) break;          // block-uniform
-        if ((tid & ~31u) + (uint32_t)r * nt >= (uint32_t)P.T1) continue;  // warp-uniform: no boundary in this warp
-        uint32_t lo = 0, m = 0;
-        if (own[r] != 0xFFFFFFFFu) {
-            lo = S.cnt[own[r]] & kPosMask;
-            m = (S.cnt[own[r] + 1] & kPosMask) - lo;
-        }
-        uint32_t inc = m;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= (uint32_t)o) inc += t;
-        }
-        uint32_t base = 0;
-        if (lane == 31 && inc) base = atomicAdd(&S.scan_tmp[32], inc);
-        base = __shfl_sync(kFull, base, 31) + inc - m;
-        for (uint32_t y = 0; y < m; ++y) lst_put(base + y, (own[r] << 16) | (uint32_t)stage[lo + y]);
-    }
-    __syncthreads();
-    const uint32_t n_list = S.scan_tmp[32];
+    const uint32_t n_list = S.scan_tmp[kListCtr];
     for (uint32_t x = tid; x < n_list; x += nt) {
-        const uint32_t e = lst_get(x) & 0xFFFFu;
+        const uint32_t ent = lst_get(x);
+        const uint32_t b = ent >> 16;
+        const uint32_t e = stage[(S.cnt[b] & kPosMask) + (ent & 0xFFFFu)];  // the member's element id
         uint32_t &slot = S.ba[ba_index(e, n8)];
         slot = tie_word(slot >> 16, secondary_key(seed, perm_id, stream, e), B);
+        lst_put(x, (b << 16) | e);
     }
     __syncthreads();
     for (uint32_t x = tid; x < n_list; x += nt) {
@@ -554,10 +614,10 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     __syncthreads();
     for (uint32_t x = tid; x < n_list; x += nt) {
         const uint32_t ent = lst_get(x);
-        stage[ent >> 16] = P.dslot2[ent & 0xFFFFu];
+        const uint32_t f = ent >> 16;
+        if (f < P.n1_eff) stage[f] = P.dslot2[ent & 0xFFFFu];
     }
-    __syncthreads();
-    // positions past the last threshold carry no partner
+    // positions past the last threshold carry no partner (disjoint from the writes above)
     for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
     __syncthreads();
 }
@@ -574,13 +634,13 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const uint32_t nmax8 = (nmax + 7) & ~7u;
     const int Bmax = B1 > B2 ? B1 : B2;
-    // shared: cnt[NB+1] | scan_tmp[33] | pad | stage[max(pb_stride, nmax8)] u16 | bounds[T1] u32 | order2[n_common] u16 |
+    // shared: cnt[NB+1] | scan_tmp[kScanTmp] | pad | stage[max(pb_stride, nmax8)] u16 | bounds[T1] u32 | order2[n_common] u16 |
     //         ba[nmax8] u32 (unless in scratch) | list_s[list_cap] u32
     // per-CTA global scratch (L2-resident): words[nmax8] | tie[nmax8] | list_g[nmax8] | ba[nmax8] (when it does not fit)
     SortShared S;
     S.cnt = reinterpret_cast<uint32_t *>(smem_raw);
     S.scan_tmp = S.cnt + (1u << Bmax) + 1;
-    size_t off = (((size_t)(1u << Bmax) + 1 + 33) * 4 + 15) & ~(size_t)15;
+    size_t off = (((size_t)(1u << Bmax) + 1 + kScanTmp) * 4 + 15) & ~(size_t)15;
     uint16_t *stage = reinterpret_cast<uint16_t *>(smem_raw + off);
     off += (size_t)(P.pb_stride > nmax8 ? P.pb_stride : nmax8) * 2;  // both are multiples of 8 entries: 16 B aligned
     uint32_t *bounds = reinterpret_cast<uint32_t *>(smem_raw + off);
@@ -1582,7 +1642,7 @@ size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool ba_in_smem) {
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
     const uint32_t nmax8 = (nmax + 7) & ~7u;
     const int Bmax = B1 > B2 ? B1 : B2;
-    size_t b = (((size_t)(1u << Bmax) + 1 + 33) * 4 + 15) & ~(size_t)15;
+    size_t b = (((size_t)(1u << Bmax) + 1 + kScanTmp) * 4 + 15) & ~(size_t)15;
     b += (size_t)(P.pb_stride > nmax8 ? P.pb_stride : nmax8) * 2;
     b += (((size_t)P.T1 * 4) + 15) & ~(size_t)15;
     const bool identical = (P.n_common == P.n1 && P.n_common == P.n2);

@@ -10,5 +10,5 @@ nvcc $F -c $src/dto_kernels.cu -o $tmp/k.o &
 nvcc $F -c $src/dto_engine.cu -o $tmp/e.o &
 wait
 mkdir -p build/variants
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so $tmp/k.o $tmp/e.o dual_threshold_optimization_b200/lib/obj/dto_host.o -cudart static -lpthread
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/variants/$name.so $tmp/k.o $tmp/e.o dual_threshold_optimization_b200/lib/obj/dto_host.o -cudart static -lpthread -ldl
 rm -rf $tmp
