@@ -407,34 +407,42 @@ def bench_single(args, cfg, dto, capi, eng, clocks, rank, world, local_rank, bar
     if n_un:
         perm_arr[0] = 0
     rec_bytes = capi.RECORD_DTYPE.itemsize
-    gather_in = torch.zeros((1 + P_max) * rec_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
-    gather_out = torch.zeros(world * (1 + P_max) * rec_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
-    host_stage = torch.zeros((1 + P_max) * rec_bytes, dtype=torch.uint8).pin_memory() if world > 1 else None
+    # host result buffer of one step: [unpermuted record, permuted records of every rank]; pinned, so the device copies
+    # land in it directly and dto_b200_empirical_pvalue reads it in place
+    host_all = torch.zeros((1 + world * P_max) * rec_bytes, dtype=torch.uint8).pin_memory()
+    all_recs = host_all.numpy().view(capi.RECORD_DTYPE)
+    my_recs = all_recs[: n_un + P] if world == 1 else np.zeros(n_un + P, dtype=capi.RECORD_DTYPE)
+    stage_in = torch.zeros(P_max * rec_bytes, dtype=torch.uint8).pin_memory() if world > 1 else None
+    gather_in = torch.zeros(P_max * rec_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
+    gather_out = torch.zeros(world * P_max * rec_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
+    uneven = args.scaling == "strong" and per_step_all % world != 0
     e2e_copy_bytes = [0, 0]
 
     def e2e_step(step_idx):
         first = 1 + (50_000 + step_idx) * per_step_all + lo
         ids_arr[n_un:] = np.arange(first, first + P, dtype=np.uint64)
-        recs = run_single_node_records((ids_arr, perm_arr), l1, l2, population, 1, [local_rank], PHILOX_SEED)
+        recs = run_single_node_records((ids_arr, perm_arr), l1, l2, population, 1, [local_rank], PHILOX_SEED, out=my_recs)
         if world == 1:
             return empirical_pvalue_struct(recs).empirical_pvalue
-        raw = recs.view(np.uint8).ravel()
-        host_stage.zero_()
-        host_stage[: raw.size] = torch.from_numpy(raw)
-        gather_in.copy_(host_stage, non_blocking=True)
+        # the records of all ranks meet on rank 0 (NCCL all-gather of the raw records: what multi_node.rs:148-160 does over MPI)
+        raw = recs[n_un:].view(np.uint8).ravel()
+        stage_in[: raw.size] = torch.from_numpy(raw)
+        gather_in.copy_(stage_in, non_blocking=True)
         dist.all_gather_into_tensor(gather_out, gather_in)
         e2e_copy_bytes[0] += gather_in.numel()
         if rank != 0:
             torch.cuda.synchronize()
             return None
-        allb = gather_out.cpu().numpy()
-        e2e_copy_bytes[1] += allb.size
-        parts = []
+        host_all[rec_bytes:].copy_(gather_out, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_copy_bytes[1] += gather_out.numel()
+        all_recs[0] = recs[0]
+        if not uneven:
+            return empirical_pvalue_struct(all_recs).empirical_pvalue
+        parts = [all_recs[:1]]
         for r in range(world):
-            rlo, rhi = shard(per_step_all, world, r) if args.scaling == "strong" else (0, P)
-            cnt = (rhi - rlo) + (1 if r == 0 else 0)
-            chunk = allb[r * (1 + P_max) * rec_bytes: r * (1 + P_max) * rec_bytes + cnt * rec_bytes]
-            parts.append(chunk.view(capi.RECORD_DTYPE))
+            rlo, rhi = shard(per_step_all, world, r)
+            parts.append(all_recs[1 + r * P_max: 1 + r * P_max + (rhi - rlo)])
         return empirical_pvalue_struct(np.concatenate(parts)).empirical_pvalue
 
     e2e_step(-1)

@@ -27,6 +27,8 @@ FLAG_PERMUTED = 0x1
 FLAG_TIE_RESOLVED = 0x2  # the host libm settled a tie set the device could not (include/dto_b200.h)
 FLAG_HOST_PVALUE = 0x4
 FLAG_PATH_FULL = 0x8
+FLAG_TIE_MINP = 0x10
+FLAG_TIE_OVERLAP = 0x20
 
 
 class DtoError(RuntimeError):
@@ -149,6 +151,8 @@ SYMBOLS = {
     "dto_b200_read_feature_list": (C.c_int, [C.c_char_p, C.POINTER(_vp)]),
     "dto_b200_feature_list_free": (None, [_vp]),
     "dto_b200_feature_list_len": (C.c_size_t, [_vp]),
+    "dto_b200_feature_list_id": (C.c_char_p, [_vp, C.c_size_t]),
+    "dto_b200_get_limits": (C.c_int, [C.POINTER(C.c_uint64 * 4)]),
     "dto_b200_compute_population_size": (C.c_int, [_vp, _vp, _vp, _u64p]),
     "dto_b200_load_lists": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "dto_b200_optimize": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, _recp]),

@@ -114,6 +114,14 @@ int main(int argc, char **argv) {
     if (dto_b200_run_single_node(l1, l2, population, task_permute.data(), task_permute.size(), devices.data(),
                                  devices.size(), seed, records.data()))
         return die("run");
+    // the reference's tie notices (optimize_main.rs:85-107) for the unpermuted task
+    if (records[0].flags & DTO_B200_FLAG_TIE_MINP) {
+        fprintf(stderr, "Multiple results with the same minimum p-value (%.15f). Choosing the result with the largest intersection size.\n",
+                records[0].pvalue);
+        if (records[0].flags & DTO_B200_FLAG_TIE_OVERLAP)
+            fprintf(stderr, "Multiple results with the same maximum intersection size (%u). Choosing an arbitrary result based on the order of thresholds.\n",
+                    records[0].intersection_size);
+    }
     dto_b200_final_result fin;
     if (dto_b200_empirical_pvalue(records.data(), records.size(), &fin)) return die("empirical_pvalue");
     size_t len = 0;

@@ -178,13 +178,15 @@ struct HostCell {
 
 // optimize_main.rs:73-116 over a handful of cells, with p re-evaluated on the host: smallest p (exact ==), then largest
 // overlap, then smallest (rank1, rank2) == smallest (row, column).  Cells with equal (K, n, k) are evaluated once.
-dto_b200_record resolve_on_host(dto_b200_ctx *ctx, const HostCell *cells, size_t n_cells, uint32_t flags) {
+dto_b200_record resolve_on_host(dto_b200_ctx *ctx, const HostCell *cells, size_t n_cells, uint32_t flags,
+                                uint32_t *n_min_out = nullptr, uint32_t *n_maxk_out = nullptr) {
     const int T2 = ctx->P.T2;
     (void)T2;
     double best_p = INFINITY;
     uint32_t best_k = 0, best_ij = 0xFFFFFFFFu;
     uint32_t lastK = ~0u, lastn = ~0u, lastk = ~0u;
     double lastp = 0.0;
+    uint32_t n_min = 0, n_maxk = 0;  // cells sharing the minimum p exactly / of those, sharing the largest overlap
     for (size_t x = 0; x < n_cells; ++x) {
         const uint32_t i = cells[x].ij >> 16, j = cells[x].ij & 0xFFFFu, k = cells[x].k;
         const uint32_t K = ctx->h_c1[i], n = ctx->h_c2[j];
@@ -195,9 +197,17 @@ dto_b200_record resolve_on_host(dto_b200_ctx *ctx, const HostCell *cells, size_t
             p = host_p(ctx, K, n, k);
             lastK = K, lastn = n, lastk = k, lastp = p;
         }
+        if (best_ij == 0xFFFFFFFFu || p < best_p) n_min = 1, n_maxk = 1;
+        else if (p == best_p) {
+            ++n_min;
+            if (k > best_k) n_maxk = 1;
+            else if (k == best_k) ++n_maxk;
+        }
         const bool better = best_ij == 0xFFFFFFFFu || p < best_p || (p == best_p && (k > best_k || (k == best_k && cells[x].ij < best_ij)));
         if (better) best_p = p, best_k = k, best_ij = cells[x].ij;
     }
+    if (n_min_out) *n_min_out = n_min;
+    if (n_maxk_out) *n_maxk_out = n_maxk;
     ctx->stats.tie_cells_host += n_cells;
     const uint32_t bi = best_ij >> 16, bj = best_ij & 0xFFFFu;
     dto_b200_record r;
@@ -229,8 +239,8 @@ int dense_task(dto_b200_ctx *ctx, const uint16_t *pbrow, uint32_t flags, dto_b20
     CUDA_TRY(launch_full_collect(P, ctx->d_H.as<uint32_t>(), ctx->d_pv.as<double>(), d_bc, d_bc + 1, ctx->d_collect.as<uint2>(), ctx->stream));
     count_launches(ctx, 6);
     ctx->stats.tasks_full += 1;
-    uint32_t head[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(head, d_bc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t head[4] = {0, 0, 0, 0};  // argmin cell, listed cells, zero-plateau cells, of those with the winning overlap
+    CUDA_TRY(cudaMemcpyAsync(head, d_bc, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     const uint32_t cnt = head[1];
     if (cnt == 0 || cnt > cells) return fail(DTO_B200_ERR_CUDA, "dense path returned an invalid tie count (%u)", cnt);
@@ -251,8 +261,19 @@ int dense_task(dto_b200_ctx *ctx, const uint16_t *pbrow, uint32_t flags, dto_b20
         if (a.k != b.k) return a.k < b.k;
         return a.ij < b.ij;
     });
-    dto_b200_record r = resolve_on_host(ctx, hc.data(), hc.size(), flags | DTO_B200_FLAG_PATH_FULL | (cnt > 1 ? DTO_B200_FLAG_TIE_RESOLVED : 0u));
+    uint32_t n_min = 0, n_maxk = 0;
+    dto_b200_record r = resolve_on_host(ctx, hc.data(), hc.size(), flags | DTO_B200_FLAG_PATH_FULL | (cnt > 1 ? DTO_B200_FLAG_TIE_RESOLVED : 0u),
+                                        &n_min, &n_maxk);
     if (cnt > 1) ctx->stats.tasks_tie_resolved += 1;
+    if (r.pvalue == 0.0 && head[2] > 0) {
+        // zero plateau: the listed cells are the argmin and the few-quanta neighbours; the plateau itself was counted on
+        // the device (exp() underflows identically on both sides)
+        n_min = head[2] + (n_min > 0 ? n_min - 1 : 0);
+        n_maxk = std::max(n_maxk, head[3]);
+    }
+    // the situations in which the reference prints its two notices (optimize_main.rs:85-107)
+    if (n_min > 1) r.flags |= DTO_B200_FLAG_TIE_MINP;
+    if (n_min > 1 && n_maxk > 1) r.flags |= DTO_B200_FLAG_TIE_OVERLAP;
     if (d_dst) {
         CUDA_TRY(cudaMemcpy(d_dst, &r, sizeof(r), cudaMemcpyHostToDevice));
         count_h2d(ctx, sizeof(r));
@@ -590,6 +611,15 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
     } else {
         return fail(DTO_B200_ERR_INVALID, "unknown option '%s'", name);
     }
+    return DTO_B200_OK;
+}
+
+int dto_b200_get_limits(dto_b200_limits *out) {
+    if (!out) return fail(DTO_B200_ERR_INVALID, "null output");
+    out->max_features_per_list = 65534;
+    out->max_thresholds_per_list = 2048;
+    out->max_population = (uint64_t)1 << 27;
+    out->max_tasks_per_call = (uint64_t)1 << 40;
     return DTO_B200_OK;
 }
 

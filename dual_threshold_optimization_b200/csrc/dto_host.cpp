@@ -320,6 +320,9 @@ int dto_b200_read_feature_list(const char *path, dto_b200_feature_list **out) {
 
 void dto_b200_feature_list_free(dto_b200_feature_list *l) { delete l; }
 size_t dto_b200_feature_list_len(const dto_b200_feature_list *l) { return l ? l->ids.size() : 0; }
+const char *dto_b200_feature_list_id(const dto_b200_feature_list *l, size_t i) {
+    return (l && i < l->ids.size()) ? l->ids[i].c_str() : nullptr;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // compute_population_size (src/dto/compute_population_size.rs:66-104)

@@ -1513,6 +1513,8 @@ __global__ void __launch_bounds__(1024) full_argmin_kernel(const Problem P, cons
 // minimum is exactly 0.0 the (possibly thousands of) other exact zeros are NOT listed: exp() underflows identically on
 // both sides, so among them the integer tie-break of full_argmin_kernel is already the reference's; only cells a few
 // subnormal quanta above zero are ambiguous then.
+// count[0] = listed cells; when the minimum is exactly 0.0: count[1] = cells on the zero plateau, count[2] = those of them
+// with the winning overlap (what the reference's two tie notices, optimize_main.rs:87-107, are about).
 __global__ void full_collect_kernel(const Problem P, const uint32_t *__restrict__ H, const double *__restrict__ pv,
                                     const uint32_t *__restrict__ best_cell, uint32_t *__restrict__ count,
                                     uint2 *__restrict__ cells_out) {
@@ -1523,6 +1525,10 @@ __global__ void full_collect_kernel(const Problem P, const uint32_t *__restrict_
     bool take = (uint32_t)cell == bc;
     if (!take) take = pb > 0.0 ? (p <= pb * (1.0 + kTieRel) + kTieAbs) : (p > 0.0 && p <= kTieAbs);
     if (take) cells_out[atomicAdd(count, 1u)] = make_uint2((uint32_t)cell, H[cell]);
+    if (pb == 0.0 && p == 0.0) {
+        atomicAdd(count + 1, 1u);
+        if (H[cell] == H[bc]) atomicAdd(count + 2, 1u);
+    }
 }
 
 // records[idx[x]] = patch[x]: host-resolved records written back into the device-resident record array
@@ -1728,7 +1734,7 @@ cudaError_t launch_full_argmin(const Problem &P, const uint32_t *H, const double
 
 cudaError_t launch_full_collect(const Problem &P, const uint32_t *H, const double *pv, const uint32_t *best_cell,
                                 uint32_t *count, uint2 *cells_out, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+    cudaError_t e = cudaMemsetAsync(count, 0, 12, st);
     if (e != cudaSuccess) return e;
     full_collect_kernel<<<(P.T1 * P.T2 + 255) / 256, 256, 0, st>>>(P, H, pv, best_cell, count, cells_out);
     return cudaGetLastError();

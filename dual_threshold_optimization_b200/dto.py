@@ -12,6 +12,30 @@ from .collections import FeatureList, PermutedRankedFeatureList, RankedFeatureLi
 from .engine import Engine
 
 
+class FeatureSets:
+    """FeatureSets::Both of the debug path (src/dto/results_objects.rs:8-12, process_threshold_pairs.rs:111-115): the two
+    thresholded feature sets of one cell, rebuilt on the host from the (permuted) lists -- the device only ever sees
+    integer slots.  Holds views, not copies: a debug grid has T1 x T2 of these."""
+
+    __slots__ = ("_ids1", "_n1", "_ids2", "_n2")
+
+    def __init__(self, ids1, n1, ids2, n2):
+        self._ids1, self._n1, self._ids2, self._n2 = ids1, n1, ids2, n2
+
+    def set1(self):
+        from .collections import Feature
+
+        return [Feature(g) for g in self._ids1[: self._n1]]
+
+    def set2(self):
+        from .collections import Feature
+
+        return [Feature(g) for g in self._ids2[: self._n2]]
+
+    def both(self):
+        return self.set1(), self.set2()
+
+
 @dataclass
 class OptimizationResultRecord:
     """src/dto/results_objects.rs:22-32 (feature_sets is FeatureSets::None on the non-debug path)."""
@@ -25,6 +49,7 @@ class OptimizationResultRecord:
     pvalue: float
     permuted: bool
     tie_resolved: bool = False  # DTO_B200_FLAG_TIE_RESOLVED: the host libm settled the optimum among ulp-close cells
+    feature_sets: Optional[FeatureSets] = None  # FeatureSets::Both when debug=True, FeatureSets::None otherwise
 
     @staticmethod
     def from_np(r) -> "OptimizationResultRecord":
@@ -82,11 +107,18 @@ def process_threshold_pairs(l1: RankedFeatureList, l2: RankedFeatureList, use_pe
     r1, r2 = l1.ranks(), l2.ranks()
     c1 = np.searchsorted(r1, t1, side="right")
     c2 = np.searchsorted(r2, t2, side="right")
+    ids1 = ids2 = None
+    if debug:  # feature sets in (permuted) position order: position j holds the gene of slot indices[j] (permuted.rs:95-99)
+        ids1, ids2 = l1.ids(), l2.ids()
+        if perm1 is not None:
+            ids1 = [ids1[k] for k in perm1]
+            ids2 = [ids2[k] for k in perm2]
     out = []
     for i in range(t1.size):
         for j in range(t2.size):
             out.append(OptimizationResultRecord(int(t1[i]), int(t2[j]), int(c1[i]), int(c2[j]), int(population_size),
-                                                int(ov[i, j]), float(pv[i, j]), permuted))
+                                                int(ov[i, j]), float(pv[i, j]), permuted,
+                                                feature_sets=FeatureSets(ids1, int(c1[i]), ids2, int(c2[j])) if debug else None))
     return out
 
 

@@ -21,14 +21,8 @@ def read_feature_list_from_file(filepath: str) -> FeatureList:
     L = capi.lib()
     capi.check(L.dto_b200_read_feature_list(str(filepath).encode(), C.byref(h)))
     try:
-        # round-trip through the text file keeps this thin: re-read the ids for the Python object
-        with open(filepath, "rb") as f:
-            data = f.read().decode()
-        lines = data.split("\n")
-        if lines and lines[-1] == "":
-            lines.pop()
-        ids = [ln[:-1].strip() if ln.endswith("\r") else ln.strip() for ln in lines]
-        assert len(ids) == L.dto_b200_feature_list_len(h)
+        n = L.dto_b200_feature_list_len(h)
+        ids = [L.dto_b200_feature_list_id(h, i).decode() for i in range(n)]  # the C reader is the only parser of the format
     finally:
         L.dto_b200_feature_list_free(h)
     return FeatureList(ids)

@@ -21,13 +21,17 @@ class Task:
 
 
 def run_single_node_records(tasks: Sequence[Task], l1: RankedFeatureList, l2: RankedFeatureList, population_size: int,
-                            num_threads: int = 1, devices: Optional[Sequence[int]] = None, seed: int = 0) -> np.ndarray:
+                            num_threads: int = 1, devices: Optional[Sequence[int]] = None, seed: int = 0,
+                            out: Optional[np.ndarray] = None) -> np.ndarray:
     if isinstance(tasks, tuple) and len(tasks) == 2 and isinstance(tasks[0], np.ndarray):
         ids, tp = np.ascontiguousarray(tasks[0], dtype=np.uint64), np.ascontiguousarray(tasks[1], dtype=np.uint8)  # (ids, permute) arrays
     else:
         ids = np.array([t.id for t in tasks], dtype=np.uint64)
         tp = np.array([1 if t.permute else 0 for t in tasks], dtype=np.uint8)
-    out = np.zeros(tp.size, dtype=capi.RECORD_DTYPE)
+    if out is None:
+        out = np.zeros(tp.size, dtype=capi.RECORD_DTYPE)
+    elif out.dtype != capi.RECORD_DTYPE or out.size < tp.size or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("out must be a contiguous RECORD_DTYPE array with one record per task")
     devs = np.ascontiguousarray(devices if devices is not None else [], dtype=np.int32)
     capi.check(
         capi.lib().dto_b200_run_tasks(
@@ -37,7 +41,7 @@ def run_single_node_records(tasks: Sequence[Task], l1: RankedFeatureList, l2: Ra
             out.ctypes.data_as(C.POINTER(capi.Record)),
         )
     )
-    return out
+    return out[: tp.size]
 
 
 def run_single_node(tasks: Sequence[Task], l1: RankedFeatureList, l2: RankedFeatureList, population_size: int,

@@ -58,8 +58,27 @@ typedef struct dto_b200_record {
                                            machine); otherwise on the device: same statrs operation order, CUDA exp(), \
                                            within ~1e-14 relative */
 #define DTO_B200_FLAG_PATH_FULL 0x8u    /* solved by the full-grid exact pipeline */
+/* On records of dto_b200_run_unpermuted (and whatever else went through the full-grid pipeline): the two situations the
+ * reference reports on stderr (optimize_main.rs:85-107).  TIE_MINP: several threshold pairs share the minimum p exactly;
+ * TIE_OVERLAP: several of them also share the largest overlap, so the smallest (rank1, rank2) was taken.  The CLI prints
+ * the reference's notices from these flags for the unpermuted task; permuted tasks do not carry them (the reference
+ * prints one notice per tied permutation, thousands of lines on a typical run). */
+#define DTO_B200_FLAG_TIE_MINP 0x10u
+#define DTO_B200_FLAG_TIE_OVERLAP 0x20u
 
 typedef struct dto_b200_ctx dto_b200_ctx;
+
+/* The implemented envelope (the reference's own types are u32 ranks / usize counts, src/collections/ranked.rs:125-134):
+ * inputs beyond it fail with DTO_B200_ERR_UNSUPPORTED, never silently.  List lengths are bounded by the 16-bit packed
+ * overlap counters and partner slots of the kernels, thresholds by the per-lane column registers of the scan (a list needs
+ * max rank > 7e8 to exceed 2048 thresholds), the population by the host-built ln-factorial table. */
+typedef struct dto_b200_limits {
+    uint64_t max_features_per_list;   /* 65 534 */
+    uint64_t max_thresholds_per_list; /* 2 048 */
+    uint64_t max_population;          /* 2^27 */
+    uint64_t max_tasks_per_call;
+} dto_b200_limits;
+int dto_b200_get_limits(dto_b200_limits *out);
 
 const char *dto_b200_last_error(void);
 const char *dto_b200_version(void);
@@ -204,6 +223,7 @@ int dto_b200_feature_list_from(const char *const *ids, size_t n, dto_b200_featur
 int dto_b200_read_feature_list(const char *path, dto_b200_feature_list **out);
 void dto_b200_feature_list_free(dto_b200_feature_list *l);
 size_t dto_b200_feature_list_len(const dto_b200_feature_list *l);
+const char *dto_b200_feature_list_id(const dto_b200_feature_list *l, size_t index);
 
 /* compute_population_size (src/dto/compute_population_size.rs:66-104); background may be NULL.
  * The reference's panics come back as DTO_B200_ERR_PANIC with the same message. */

@@ -885,3 +885,53 @@ def test_multi_gpu_product_allgather_over_nccl(engine):
     for r in range(world):
         assert isinstance(got[r], np.ndarray), got[r]
         assert np.array_equal(got[r], want)
+
+
+def test_debug_feature_sets_and_tie_notices(engine, built, tmp_path):
+    """debug=true rebuilds FeatureSets::Both on the host (process_threshold_pairs.rs:111-115): the sets of every cell
+    intersect in exactly the overlap the device counted -- also under permutation.  And the unpermuted record flags the
+    situations in which the reference prints its tie notices (optimize_main.rs:85-107), which the CLI then prints."""
+    import subprocess
+
+    ids1, r1, ids2, r2, bg = H.load_test_data()
+    l1, l2 = dto.RankedFeatureList.from_(ids1, r1), dto.RankedFeatureList.from_(ids2, r2)
+    p1, p2 = dto.PermutedRankedFeatureList(l1, seed=1), dto.PermutedRankedFeatureList(l2, seed=2)
+    for perm in (False, (p1, p2)):
+        recs = dto.optimize(l1, l2, perm, 30, debug=True, engine=engine)
+        assert len(recs) == 900
+        for r in recs[::37]:
+            s1, s2 = r.feature_sets.both()
+            assert len(s1) == r.set1_len and len(s2) == r.set2_len
+            assert len(set(f.id() for f in s1) & set(f.id() for f in s2)) == r.intersection_size
+        if perm:
+            assert [f.id() for f in recs[5 * 30].feature_sets.set1()] == [f.id() for f in p1.get_feature_set_by_threshold(int(l1.thresholds()[5]))]
+    assert dto.optimize(l1, l2, False, 30, engine=engine).feature_sets is None
+    # identical lists: the p-value underflows to 0.0 on a plateau of cells, several with the same (largest) overlap? no:
+    # overlap grows along the diagonal, so exactly one cell has the largest one -> first notice only
+    n = 3000
+    a, ra, b, rb = H.synthetic_pair(n, 4, 0.0)
+    la, lb = dto.RankedFeatureList.from_(a, ra), dto.RankedFeatureList.from_(b, rb)
+    engine.load_lists(la, lb, n)
+    rec = engine.run_unpermuted()
+    o1, o2 = H.oracle_lists(a, ra, b, rb)
+    ref = O.grid_int(o1, o2, n)
+    zero = ref.p == 0.0
+    kmax = int(ref.overlap[zero].max())
+    f = int(rec["flags"])
+    assert bool(f & dto._capi.FLAG_TIE_MINP) == (int(zero.sum()) > 1)
+    assert bool(f & dto._capi.FLAG_TIE_OVERLAP) == (int((ref.overlap[zero] == kmax).sum()) > 1)
+    # ranks with gaps repeat set sizes at consecutive thresholds: the minimum is shared by cells with equal (K, n, k)
+    ids = H.ids_for(60, "q")
+    rg = (np.arange(60, dtype=np.uint32) * 7 + 3)
+    f1, f2 = tmp_path / "a.csv", tmp_path / "b.csv"
+    f1.write_text("".join(f"{g},{r}\n" for g, r in zip(ids, rg)))
+    f2.write_text("".join(f"{g},{r}\n" for g, r in zip(ids, rg)))
+    out = subprocess.run([dto._capi.CLI_PATH, "-1", str(f1), "-2", str(f2), "-p", "10", "--seed", "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    o = H.oracle_lists(ids, rg, ids, rg)
+    fr = O.process_threshold_pairs_faithful(o[0], o[1], 60)
+    pmin = fr["pvalue"].min()
+    ties = fr[fr["pvalue"] == pmin]
+    assert ties.size > 1 and "Multiple results with the same minimum p-value (%.15f)" % pmin in out.stderr
+    kmx = ties["intersection_size"].max()
+    assert ("Multiple results with the same maximum intersection size (%d)" % kmx in out.stderr) == (int((ties["intersection_size"] == kmx).sum()) > 1)

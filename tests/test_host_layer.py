@@ -228,3 +228,13 @@ def test_oracle_batch_equals_per_task_oracle():
         ob = O.grid_int(o1, o2, 400, None, p1[t], p2[t], want_overlap=False, want_p=False).best
         assert all(int(b[t][f]) == int(ob[f]) for f in ("rank1", "rank2", "set1_len", "set2_len", "intersection_size"))
         assert float(b[t]["pvalue"]) == float(ob["pvalue"])
+
+
+def test_limits_query_and_feature_list_reader(tmp_path):
+    lim = (C.c_uint64 * 4)()
+    capi.check(capi.lib().dto_b200_get_limits(C.byref(lim)))
+    assert list(lim)[:3] == [65534, 2048, 1 << 27]
+    p = tmp_path / "bg.txt"
+    p.write_text(" a \r\nb\n\n c\n")
+    bg = dto.read_feature_list_from_file(str(p))
+    assert bg.ids() == ["a", "b", "", "c"]  # every line counts, blank ones too (read_feature_list_from_file.rs:48-52)
