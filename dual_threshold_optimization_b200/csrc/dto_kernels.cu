@@ -1169,7 +1169,7 @@ __device__ __noinline__ void finish_task(const Problem &P, Rare &R, int task, in
 template <int CH>
 struct RowState {
     uint32_t qn;             // warp-uniform copy of the queue length (refreshed only after rows that pushed something)
-    uint32_t lo, cbase;      // next list-1 position; oldest resident chunk of the partner-slot ring
+    uint32_t g, pend;        // first list-1 position of the current 32-position group; lanes whose element is not binned yet
     int i, level;            // next row; screen level
 };
 
@@ -1200,15 +1200,28 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
     const uint16_t *ring = reinterpret_cast<const uint16_t *>(wbase + L::d_bytes + L::q_bytes + 16 + (size_t)L::CAP * sizeof(Cand));
     const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t n_chunks = P.pb_stride / kChunk;
-    uint32_t qn = st.qn, lo = st.lo, cbase = st.cbase;
+    uint32_t qn = st.qn, g = st.g;
     int i = st.i;
     const int level = st.level;
-    auto advance_ring = [&]() {  // chunk cbase is consumed: cbase+2 must have landed, refill the freed slot
-        ++cbase;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // The partner slots stream through the warp in groups of 32 consecutive list-1 positions, one element per lane,
+    // independent of the row structure: a lane decodes its element ONCE (histogram word, which half) and bins it as soon
+    // as the row loop reaches the row the position belongs to.  Rows shorter than a group -- most rows: the threshold
+    // series grows by 1 % per step -- then cost one predicated atomic instead of a ring read, a decode and a loop each.
+    // cp.async ring: chunk q (kChunk positions) is consumed while q+1 and q+2 are in flight or landed.
+    auto enter_chunk = [&](uint32_t q) {
+        ring_issue_chunk(row, n_chunks, ring_addr, lane, q + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
         __syncwarp();
-        ring_issue_chunk(row, n_chunks, ring_addr, lane, cbase + 2);
     };
+    uint32_t cpos = g + (uint32_t)lane, coff, cadd;
+    bool pend = ((st.pend >> lane) & 1u) != 0u;
+    auto load_elem = [&]() {
+        // kNoSlot (partner beyond the last list-2 threshold) lands in a sink word past the histogram
+        const uint32_t slot = ring[cpos & (kRing - 1)];
+        coff = min(slot & 0xFFFCu, L::dummy_off);
+        cadd = (slot & 1u) * 0xFFFFu + 1u;
+    };
+    load_elem();
     // this lane's words of the current row of critical overlaps (level `level`, row i), advanced row by row
     const uint4 *__restrict__ kr =
         reinterpret_cast<const uint4 *>(P.kcrit + ((size_t)level * P.T1 + i) * P.T2pad) + lane;
@@ -1219,8 +1232,9 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
     {
         for (; i < T1; ++i) {
             const uint32_t hi = s_c1[i];
-            // critical overlaps of this row at the current screen level, two columns per 32-bit load (in flight during
-            // the scatter)
+            // critical overlaps of this row at the current screen level: ceil(CH/8) coalesced 128-bit loads per lane, in
+            // flight during the scatter.  (Requesting row i+1 one row ahead -- a twice-unrolled body with two register
+            // sets -- was measured 13 % SLOWER at N = 20 000, like the software pipelining tried in round 1.)
             uint32_t kc2[KV * 4];
 #pragma unroll
             for (int v = 0; v < KV; ++v) {
@@ -1228,22 +1242,18 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
                 kc2[4 * v] = t.x, kc2[4 * v + 1] = t.y, kc2[4 * v + 2] = t.z, kc2[4 * v + 3] = t.w;
             }
             kr += kr_step;
-            // (1) bin this row's genes: position -> partner's column slot, privatised per warp.  Positions below
-            // (cbase + 2) * kChunk are resident in the ring.
-            if ((lo / kChunk) > cbase) advance_ring();  // chunk cbase is consumed (once per row is enough to stay ahead)
+            // (1) bin this row's genes: every element of the stream below the row's end position, privatised per warp
             for (;;) {
-                const uint32_t res = (cbase + 2) * kChunk, lim = hi < res ? hi : res;
-#pragma unroll 1
-                for (uint32_t pos = lo + lane; pos < lim; pos += 32) {
-                    // kNoSlot (partner beyond the last list-2 threshold) lands in a sink word past the histogram
-                    const uint32_t slot = ring[pos & (kRing - 1)];
-                    const uint32_t off = min(slot & 0xFFFCu, L::dummy_off);
-                    atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(D) + off),
-                              (slot & 1u) * 0xFFFFu + 1u);
+                if (pend && cpos < hi) {
+                    atomicAdd(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(D) + coff), cadd);
+                    pend = false;
                 }
-                lo = lim;
-                if (lo >= hi) break;
-                advance_ring();
+                if (g + 32 > hi) break;  // the group reaches past this row: its remaining elements belong to later rows
+                g += 32;
+                cpos += 32;
+                if ((g & (kChunk - 1)) == 0) enter_chunk(g / kChunk);
+                load_elem();
+                pend = true;
             }
             __syncwarp();
             // (2) 2-D inclusive prefix, everything packed (two 16-bit counts per word; no field ever exceeds 65534).  The
@@ -1339,8 +1349,8 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
         }
     }
     st.qn = qn;
-    st.lo = lo;
-    st.cbase = cbase;
+    st.g = g;
+    st.pend = __ballot_sync(kFull, pend);
     st.i = i;
 }
 
@@ -1396,16 +1406,17 @@ scan_kernel(const __grid_constant__ Problem P, const uint16_t *__restrict__ pb, 
         R.lane = lane;
 
         RowState<CH> st;
-        st.qn = st.lo = st.cbase = 0;
+        st.qn = st.g = 0;
+        st.pend = kFull;
         st.i = st.level = 0;
         // partner-slot row staged through shared memory with cp.async: chunk c = kChunk positions, one 8 B copy per
-        // lane; chunks cbase and cbase+1 are resident, cbase+2 is in flight (ring of 4 chunks)
+        // lane; chunk 0 must have landed before the row loop starts, chunks 1 and 2 stay in flight (ring of 4 chunks)
         const uint32_t n_chunks = P.pb_stride / kChunk;
         ring_issue_chunk(row, n_chunks, ring_addr, lane, 0);
         ring_issue_chunk(row, n_chunks, ring_addr, lane, 1);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
         ring_issue_chunk(row, n_chunks, ring_addr, lane, 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
         // The row loop lives in scan_rows and is call-free: when the queue holds a full chunk it returns to the
         // (out-of-line) drain and is re-entered, so the column state is only saved/restored around that rare trip.
         while (st.i < P.T1) {
