@@ -9,4 +9,4 @@ from .read import read_feature_list_from_file, read_ranked_feature_list_from_csv
 from .run import Task, run_multi_gpu, run_pairs, run_single_node  # noqa: F401
 from .stat_operations import empirical_pvalue, fdr, hypergeometric_pvalue, intersect_genes  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

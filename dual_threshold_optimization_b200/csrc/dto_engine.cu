@@ -518,7 +518,7 @@ size_t group_task_capacity(const dto_b200_ctx *ctx) { return ctx->has_problem ? 
 extern "C" {
 
 const char *dto_b200_last_error(void) { return g_last_error.c_str(); }
-const char *dto_b200_version(void) { return "dto-b200 0.1.0 (sm_100a)"; }
+const char *dto_b200_version(void) { return "dto-b200 0.2.0 (sm_100a)"; }
 
 int dto_b200_device_count(int *count_out) {
     if (!count_out) return fail(DTO_B200_ERR_INVALID, "null count_out");
@@ -831,24 +831,20 @@ int dto_b200_set_problem(dto_b200_ctx *ctx, const uint32_t *ranks1, size_t n1, c
     CUDA_TRY(ctx->d_counts.ensure(cells * 4));
     CUDA_TRY(ctx->d_meta.ensure(cells * 8));
     CUDA_TRY(launch_build_kcrit(P, ctx->d_kcrit.as<uint16_t>(), ctx->d_counts.as<uint32_t>(), ctx->d_meta.as<uint2>(), ctx->stream));
-    std::vector<uint32_t> counts(cells);
-    CUDA_TRY(cudaMemcpyAsync(counts.data(), ctx->d_counts.p, cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // offsets of the per-cell table segments = exclusive scan of the counts, on the device; only the total comes back
+    // (it sizes the table)
+    unsigned long long *d_total = ctx->d_counters.as<unsigned long long>() + 6;
+    CUDA_TRY(launch_scan_counts(ctx->d_counts.as<uint32_t>(), (int)cells, d_total, ctx->stream));
+    unsigned long long total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    uint64_t total = 0;
-    for (size_t c = 0; c < cells; ++c) {
-        const uint32_t v = counts[c];
-        counts[c] = (uint32_t)total;
-        total += v;
-    }
-    if (total > 0xFFFFFFFFull) return fail(DTO_B200_ERR_UNSUPPORTED, "log-p table too large (%llu entries)", (unsigned long long)total);
+    if (total > 0xFFFFFFFFull) return fail(DTO_B200_ERR_UNSUPPORTED, "log-p table too large (%llu entries)", total);
     CUDA_TRY(ctx->d_lptab.ensure((size_t)(total ? total : 1) * 8));
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_counts.p, counts.data(), cells * 4, cudaMemcpyHostToDevice, ctx->stream));
     P.cellmeta = ctx->d_meta.as<uint2>();
     P.lptab = ctx->d_lptab.as<double>();
     CUDA_TRY(launch_fill_lptab(P, ctx->d_counts.as<uint32_t>(), ctx->d_meta.as<uint2>(), ctx->d_lptab.as<double>(), ctx->stream));
-    count_launches(ctx, 3);
-    count_h2d(ctx, cells * 4);
-    count_d2h(ctx, cells * 4);
+    count_launches(ctx, 4);
+    count_d2h(ctx, 8);
     ctx->stats.lptab_entries = total;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     ctx->tab_N = population;

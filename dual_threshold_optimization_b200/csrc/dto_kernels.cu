@@ -15,6 +15,7 @@
 #include "dto_host_math.hpp"  // kTieRel / kTieAbs: the ambiguity window shared with the host resolver
 
 #include <algorithm>
+#include <atomic>
 
 namespace dto {
 
@@ -121,6 +122,43 @@ __global__ void __launch_bounds__(256) build_kcrit_kernel(const Problem P, uint1
 
 __global__ void fill_u16_kernel(uint16_t *__restrict__ dst, size_t n, uint16_t v) {
     for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) dst[x] = v;
+}
+
+// exclusive scan of counts[0..n) in place (one CTA of 1024 threads: n is a few hundred thousand words, once per problem);
+// *total_out = the sum, saturated at 0xFFFFFFFF
+__global__ void __launch_bounds__(1024) exclusive_scan_counts_kernel(uint32_t *__restrict__ counts, int n,
+                                                                     unsigned long long *__restrict__ total_out) {
+    __shared__ unsigned long long wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int b = min(tid * per, n), e = min(b + per, n);
+    unsigned long long sum = 0;
+    for (int x = b; x < e; ++x) sum += counts[x];
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long v = wsum[lane], s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(kFull, s, o);
+            if (lane >= o) s += u;
+        }
+        wsum[lane] = s - v;
+        if (lane == 31) *total_out = s;
+    }
+    __syncthreads();
+    unsigned long long run = wsum[w] + inc - sum;
+    for (int x = b; x < e; ++x) {
+        const uint32_t v = counts[x];
+        counts[x] = (uint32_t)(run > 0xFFFFFFFFull ? 0xFFFFFFFFull : run);
+        run += v;
+    }
 }
 
 __global__ void set_meta_offsets_kernel(int cells, const uint32_t *__restrict__ offsets, uint2 *__restrict__ meta) {
@@ -498,33 +536,39 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     };
     auto lst_get = [&](uint32_t x) -> uint32_t { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
     // The bucket a row boundary p cuts (off[b] < p < off[b+1]), per boundary; T1 <= 2048 = 2 boundaries per thread.  The
-    // thread whose boundary is the FIRST one inside a bucket (the previous boundary lies at or before its start) owns it:
-    // it flags the bucket (bit 31 of its offset; one owner per bucket, so a plain store -- concurrent searches mask the
-    // bit out) and reserves one list entry per member, (bucket << 16 | member index); the member's element id is only
-    // known after the placement, which leaves it in the staged row.
+    // thread whose boundary is the FIRST one inside a bucket (the previous boundary lies at or before its start) owns it.
+    uint32_t own[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, own_m[2] = {0u, 0u}, own_lo[2] = {0u, 0u};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-        if ((uint32_t)r * nt >= (uint32_t)P.T1) break;                    // block-uniform
-        if ((tid & ~31u) + (uint32_t)r * nt >= (uint32_t)P.T1) continue;  // warp-uniform: no boundary in this warp
         const uint32_t x = tid + (uint32_t)r * nt;
-        uint32_t own = 0xFFFFFFFFu, m = 0;
         if (x < (uint32_t)P.T1) {
             const uint32_t p = bounds[x];
             if (p > 0 && p < n) {
                 uint32_t lo = 0, hi = NB;  // largest b with off[b] <= p: the (non-empty) bucket holding position p
                 while (hi - lo > 1) {
                     const uint32_t mid = (lo + hi) >> 1;
-                    if ((S.cnt[mid] & kPosMask) <= p) lo = mid;
+                    if (S.cnt[mid] <= p) lo = mid;
                     else hi = mid;
                 }
-                const uint32_t start = S.cnt[lo] & kPosMask;
+                const uint32_t start = S.cnt[lo];
                 if (start < p && (x == 0 || bounds[x - 1] <= start)) {
-                    own = lo;
-                    m = (S.cnt[lo + 1] & kPosMask) - start;
-                    S.cnt[lo] = start | 0x80000000u;
+                    own[r] = lo;
+                    own_lo[r] = start;
+                    own_m[r] = S.cnt[lo + 1] - start;
                 }
             }
         }
+    }
+    __syncthreads();
+    // owners flag their bucket (bit 31 of its offset; one owner per bucket: a plain store) and reserve one list entry per
+    // member, (bucket << 16 | member index) -- the member's element id is only known after the placement, which leaves
+    // it in the staged row.  One warp-aggregated reservation per warp that owns anything.
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if ((uint32_t)r * nt >= (uint32_t)P.T1) break;                    // block-uniform
+        if ((tid & ~31u) + (uint32_t)r * nt >= (uint32_t)P.T1) continue;  // warp-uniform: no boundary in this warp
+        const uint32_t m = own_m[r];
+        if (m) S.cnt[own[r]] = own_lo[r] | 0x80000000u;
         uint32_t inc = m;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -534,7 +578,7 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         uint32_t base = 0;
         if (lane == 31 && inc) base = atomicAdd(&S.scan_tmp[kListCtr], inc);
         base = __shfl_sync(kFull, base, 31) + inc - m;
-        for (uint32_t y = 0; y < m; ++y) lst_put(base + y, (own << 16) | y);
+        for (uint32_t y = 0; y < m; ++y) lst_put(base + y, (own[r] << 16) | y);
     }
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
@@ -1579,11 +1623,18 @@ __global__ void hbm_copy_probe_kernel(const uint4 *__restrict__ src, uint4 *__re
 // =====================================================================================================
 // launchers
 // =====================================================================================================
-static int max_optin_smem() {
+// opts a kernel into the device's maximum dynamic shared memory, once per device (bit d of `done` = device d is set up)
+static cudaError_t set_max_smem_once(const void *kern, std::atomic<uint64_t> &done) {
     int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return v;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 template <int CH, bool SWAR>
@@ -1593,9 +1644,10 @@ static cudaError_t launch_scan_t(const Problem &P, const uint16_t *pb, int n_tas
     using L = ScanLayout<CH>;
     const size_t smem = (((size_t)P.T1 * 4 + 15) & ~(size_t)15) + (size_t)warps * L::per_warp;
     auto kern = scan_kernel<CH, SWAR>;
-    // always the device maximum: the attribute is per function and process-wide, and several contexts (host threads)
-    // may launch the same instantiation with different sizes concurrently
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
+    // always the device maximum: the attribute is per function and device, and several contexts (host threads) may launch
+    // the same instantiation with different sizes concurrently.  Set once per (instantiation, device).
+    static std::atomic<uint64_t> done{0};
+    cudaError_t e = set_max_smem_once(reinterpret_cast<const void *>(kern), done);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, st>>>(P, pb, n_tasks, n_plain, flags, out, status, counters, task_stats);
     return cudaGetLastError();
@@ -1643,6 +1695,11 @@ cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *coun
     e = cudaMemsetAsync(meta, 0, (size_t)cells * sizeof(uint2), st);
     if (e != cudaSuccess) return e;
     build_kcrit_kernel<<<(cells + 255) / 256, 256, 0, st>>>(P, kcrit, 0, counts, meta, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_counts(uint32_t *counts, int n, unsigned long long *total_out, cudaStream_t st) {
+    exclusive_scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n, total_out);
     return cudaGetLastError();
 }
 
@@ -1695,7 +1752,8 @@ cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, const uint64_t *s
     const size_t list_cap = std::min<size_t>((smem_limit - base) / 4 & ~(size_t)3, (nmax + 7) & ~7u);
     const size_t smem = base + list_cap * 4;
     auto kern = ba_in_smem ? sigma_sort_kernel<false> : sigma_sort_kernel<true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin_smem());
+    static std::atomic<uint64_t> done_a{0}, done_b{0};
+    cudaError_t e = set_max_smem_once(reinterpret_cast<const void *>(kern), ba_in_smem ? done_a : done_b);
     if (e != cudaSuccess) return e;
     kern<<<grid, kSigmaThreads, smem, st>>>(P, seed, seeds, seg ? seg : 1u, first_id, n_tasks, B1, B2, pb, pairing_out, scratch,
                                             (uint32_t)list_cap);

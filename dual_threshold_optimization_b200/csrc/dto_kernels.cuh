@@ -28,6 +28,7 @@ size_t sigma_smem_bytes(const Problem &P, int B1, int B2, bool ba_in_smem);
 size_t sigma_scratch_words(const Problem &P);
 
 cudaError_t launch_build_kcrit(const Problem &P, uint16_t *kcrit, uint32_t *counts, uint2 *meta, cudaStream_t st);
+cudaError_t launch_scan_counts(uint32_t *counts, int n, unsigned long long *total_out, cudaStream_t st);
 cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *meta, double *lptab, cudaStream_t st);
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, const uint64_t *seeds, uint32_t seg, uint64_t first_id,
                               int n_tasks, uint16_t *pb, uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit,

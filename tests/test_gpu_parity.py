@@ -248,10 +248,18 @@ def test_degenerate_and_error_paths(engine):
     # empty list -> no thresholds -> unwrap panic in the reference
     with pytest.raises(dto.DtoPanic):
         engine.load_lists(dto.RankedFeatureList.from_([], []), l2, 4)
+    # the standalone evaluator maps the same condition to the same panic (hypergeometric_pvalue.rs:40-41)
+    with pytest.raises(dto.DtoPanic):
+        engine.hypergeometric_pvalues([10, 10], [3, 11], [4, 4], [1, 1])
+    with pytest.raises(dto.DtoError):
+        engine.set_option("levels", 1)  # fewer than two screen levels certify nothing
     # not a permutation
     engine.load_lists(l1, l2, 4)
     with pytest.raises(dto.DtoError):
         engine.run_permuted_indices(np.array([[0, 0, 1]], np.uint32), np.array([[0, 1, 2]], np.uint32))
+    with pytest.raises(dto.DtoError):  # out-of-range entries are reported, never dereferenced
+        engine.run_permuted_indices(np.array([[0, 1, 2]], np.uint32), np.array([[0, 7, 4000000000]], np.uint32))
+    assert engine.run_permuted_indices(np.array([[2, 0, 1]], np.uint32), np.array([[1, 2, 0]], np.uint32)).size == 1  # context still healthy
     # duplicate ids are rejected (documented deviation)
     with pytest.raises(dto.DtoError):
         engine.load_lists(dto.RankedFeatureList.from_(["a", "a"], [1, 2]), l2, 4)
