@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--ref-row-stride", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--sigma-ctas", type=int, default=0, help="pairing kernel CTAs per SM: 0 = library default, 1 or 2 = force (A/B)")
     ap.add_argument("--cpu-worker", default="", choices=["", "baseline", "reference"], help=argparse.SUPPRESS)
     args = ap.parse_args()
 
@@ -301,6 +302,8 @@ def main():
     eng = dto.Engine(local_rank)  # raises without a GPU: there is no CPU path to fall back to
     if args.batch:
         eng.set_option("batch", args.batch)
+    if args.sigma_ctas:
+        eng.set_option("sigma_ctas", args.sigma_ctas)
     clocks = ClockSampler(local_rank)
 
     # the product's own NCCL all-gather (dto_b200_allgather_minima): rank 0 makes the unique id, torch's store carries it

@@ -130,6 +130,7 @@ struct dto_b200_ctx {
     int opt_batch = 0;  // 0 = auto
     int opt_warps = kScanThreads / 32;
     int opt_levels = 32;
+    int opt_sigma_ctas = 0;  // pairing kernel: 0 = choose, 1 = one 1024-thread CTA per SM, 2 = two 512-thread CTAs per SM
     dto_b200_stats stats{};
 };
 
@@ -461,7 +462,7 @@ int run_pair_group(dto_b200_ctx *ctx, const int32_t *slot_maps, const uint64_t *
         CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
         CUDA_TRY(launch_sigma_sort(P, 0, ctx->d_seeds.as<uint64_t>(), (uint32_t)perms, 1, (int)(G * perms),
                                    ctx->d_pb.as<uint16_t>() + G * P.pb_stride, nullptr, ctx->d_words.as<uint32_t>(),
-                                   ctx->smem_optin, (int)std::min<size_t>(G * perms, (size_t)sigma_grid_max), ctx->stream));
+                                   ctx->smem_optin, ctx->sm_count, ctx->opt_sigma_ctas, ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
         count_launches(ctx, 1);
     }
@@ -601,6 +602,9 @@ int dto_b200_set_option(dto_b200_ctx *ctx, const char *name, int64_t value) {
         ctx->opt_swar = value != 0;
     } else if (s == "table_cache") {
         ctx->opt_table_cache = value != 0;
+    } else if (s == "sigma_ctas") {
+        if (value < 0 || value > 2) return fail(DTO_B200_ERR_INVALID, "sigma_ctas must be 0, 1 or 2");
+        ctx->opt_sigma_ctas = (int)value;
     } else if (s == "task_stats") {
         ctx->opt_task_stats = value != 0;
     } else if (s == "levels") {
@@ -944,7 +948,7 @@ static int run_philox_common(dto_b200_ctx *ctx, uint64_t seed, uint64_t first, s
         CUDA_TRY(ctx->d_pb.ensure((size_t)n * P.pb_stride * 2));
         CUDA_TRY(cudaEventRecord(ctx->ev[2], ctx->stream));
         CUDA_TRY(launch_sigma_sort(P, seed, nullptr, 0, first + done, n, ctx->d_pb.as<uint16_t>(), nullptr, words_scratch,
-                                   ctx->smem_optin, std::min(n, sigma_grid_max), ctx->stream));
+                                   ctx->smem_optin, ctx->sm_count, ctx->opt_sigma_ctas, ctx->stream));
         CUDA_TRY(cudaEventRecord(ctx->ev[3], ctx->stream));
         count_launches(ctx, 1);
         rc = run_tasks(ctx, n, DTO_B200_FLAG_PERMUTED);
@@ -1001,7 +1005,7 @@ int dto_b200_philox_pairing(dto_b200_ctx *ctx, uint64_t seed, uint64_t perm_id, 
     CUDA_TRY(ctx->d_pair.ensure((size_t)(P.n1 ? P.n1 : 1) * 4));
     CUDA_TRY(cudaMemsetAsync(ctx->d_pair.p, 0xFF, (size_t)(P.n1 ? P.n1 : 1) * 4, ctx->stream));
     CUDA_TRY(launch_sigma_sort(P, seed, nullptr, 0, perm_id, 1, ctx->d_pb.as<uint16_t>(), ctx->d_pair.as<uint32_t>(), words_scratch,
-                               ctx->smem_optin, 1, ctx->stream));
+                               ctx->smem_optin, ctx->sm_count, 1, ctx->stream));
     count_launches(ctx, 1);
     CUDA_TRY(cudaMemcpyAsync(pos2_of_pos1_out, ctx->d_pair.p, (size_t)P.n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));

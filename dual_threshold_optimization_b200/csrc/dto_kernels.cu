@@ -191,7 +191,7 @@ struct SortShared {
 };
 
 constexpr uint32_t kPosMask = 0x7FFFFFFFu;
-constexpr int kListCtr = 128, kScanTmp = 129;
+constexpr int kListCtr = 256, kScanTmp = 257;  // block-scan partials: up to 8 slices x 32 warps; then the list counter
 
 __device__ __forceinline__ void philox_keys(uint32_t (&out)[4], uint64_t seed, uint64_t perm_id, uint32_t stream,
                                             uint32_t block) {
@@ -346,7 +346,8 @@ __device__ void block_exclusive_scan_sliced(uint32_t *a, uint32_t *tmp) {
 
 __device__ void block_exclusive_scan(uint32_t *a, uint32_t len, uint32_t *tmp) {
     const uint32_t nt = blockDim.x;
-    if (len == 16 * nt) block_exclusive_scan_sliced<4>(a, tmp);
+    if (len == 32 * nt) block_exclusive_scan_sliced<8>(a, tmp);
+    else if (len == 16 * nt) block_exclusive_scan_sliced<4>(a, tmp);
     else if (len == 8 * nt) block_exclusive_scan_sliced<2>(a, tmp);
     else if (len == 4 * nt) block_exclusive_scan_sliced<1>(a, tmp);
     else block_exclusive_scan_t<0>(a, len, tmp);
@@ -448,6 +449,14 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ uint4 ldg128_plain(const uint32_t *p) {  // data written by this kernel: no read-only path
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg128(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
 }
@@ -467,11 +476,18 @@ __device__ __forceinline__ void block_zero_counters_fast(const SortShared &S, in
 
 // Pass 1 of the row-wise variant (S.ba in shared memory): same result as block_bucket_keys, branch-free per element.
 // Blocks of 8 elements that lie entirely below n take the lean path; the one partial block (n % 8 != 0) is checked.
+template <bool BA_SHARED>
 __device__ __forceinline__ void block_bucket_keys_lean(const SortShared &S, uint32_t n, int B, uint64_t seed,
                                                        uint64_t perm_id, uint32_t stream) {
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t n8 = (n + 7) >> 3, full = n >> 3;
-    const uint32_t cnt_a = smem_addr(S.cnt), ba_a = smem_addr(S.ba);
+    const uint32_t cnt_a = smem_addr(S.cnt), ba_a = BA_SHARED ? smem_addr(S.ba) : 0u;
+    // (key16 | arrival) words: in shared memory, or -- so that two CTAs fit one SM at N = 20 000 -- in the CTA's global
+    // scratch (L2-resident; written here and read by the placement with coalesced 128-bit accesses)
+    auto put_ba = [&](uint32_t vec, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        if constexpr (BA_SHARED) sts128(ba_a + vec * 16, a, b, c, d);
+        else stg128(S.ba + (size_t)vec * 4, a, b, c, d);
+    };
     const uint32_t sh = 32u - (uint32_t)B;  // bucket of the key in the HIGH half of a Philox word: w >> sh
     for (uint32_t c = tid; c < full; c += nt) {
         uint32_t key[4];
@@ -486,8 +502,8 @@ __device__ __forceinline__ void block_bucket_keys_lean(const SortShared &S, uint
             v[2 * h] = wl | a0;
             v[2 * h + 1] = (w & 0xFFFF0000u) | a1;
         }
-        sts128(ba_a + c * 16, v[0], v[1], v[2], v[3]);
-        sts128(ba_a + (n8 + c) * 16, v[4], v[5], v[6], v[7]);
+        put_ba(c, v[0], v[1], v[2], v[3]);
+        put_ba(n8 + c, v[4], v[5], v[6], v[7]);
     }
     if (full < n8 && tid == (full % nt)) {  // the partial block
         const uint32_t c = full;
@@ -501,8 +517,8 @@ __device__ __forceinline__ void block_bucket_keys_lean(const SortShared &S, uint
             v[q] = k16 << 16;
             if (e < n) v[q] |= atoms_inc(cnt_a + ((k16 >> (16 - B)) << 2));
         }
-        sts128(ba_a + c * 16, v[0], v[1], v[2], v[3]);
-        sts128(ba_a + (n8 + c) * 16, v[4], v[5], v[6], v[7]);
+        put_ba(c, v[0], v[1], v[2], v[3]);
+        put_ba(n8 + c, v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
     block_exclusive_scan(S.cnt, 1u << B, S.scan_tmp);
@@ -520,11 +536,11 @@ __device__ __forceinline__ void block_bucket_keys_lean(const SortShared &S, uint
 // select, one 16-bit store); everything about boundary buckets happens on the side: the thread that owns the FIRST
 // boundary inside such a bucket lists its members afterwards (they sit in the staged row), and the ~6 % of elements on
 // that list are then ranked by all threads.
-template <bool BA_SHARED>
+template <bool BA_SHARED, int NT>
 __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const uint32_t *bounds, uint32_t n, int B,
                                     uint64_t seed, uint64_t perm_id, uint32_t stream, uint16_t *stage) {
-    if constexpr (BA_SHARED) block_bucket_keys_lean(S, n, B, seed, perm_id, stream);
-    else block_bucket_keys(S, n, B, seed, perm_id, stream, true);  // the kernel zeroes the counters during the copy-out
+    constexpr int NBND = 2048 / NT;  // row boundaries per thread (T1 <= 2048)
+    block_bucket_keys_lean<BA_SHARED>(S, n, B, seed, perm_id, stream);
     const uint32_t NB = 1u << B;
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
     const uint32_t lane = tid & 31u;
@@ -537,9 +553,10 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     auto lst_get = [&](uint32_t x) -> uint32_t { return x < S.list_cap ? S.list_s[x] : S.list_g[x]; };
     // The bucket a row boundary p cuts (off[b] < p < off[b+1]), per boundary; T1 <= 2048 = 2 boundaries per thread.  The
     // thread whose boundary is the FIRST one inside a bucket (the previous boundary lies at or before its start) owns it.
-    uint32_t own[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, own_m[2] = {0u, 0u}, own_lo[2] = {0u, 0u};
+    uint32_t own[NBND], own_m[NBND], own_lo[NBND];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < NBND; ++r) {
+        own[r] = 0xFFFFFFFFu, own_m[r] = 0u, own_lo[r] = 0u;
         const uint32_t x = tid + (uint32_t)r * nt;
         if (x < (uint32_t)P.T1) {
             const uint32_t p = bounds[x];
@@ -564,7 +581,7 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     // member, (bucket << 16 | member index) -- the member's element id is only known after the placement, which leaves
     // it in the staged row.  One warp-aggregated reservation per warp that owns anything.
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < NBND; ++r) {
         if ((uint32_t)r * nt >= (uint32_t)P.T1) break;                    // block-uniform
         if ((tid & ~31u) + (uint32_t)r * nt >= (uint32_t)P.T1) continue;  // warp-uniform: no boundary in this warp
         const uint32_t m = own_m[r];
@@ -583,17 +600,20 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
     const uint32_t steps = 2 * n8;
-    if constexpr (BA_SHARED) {
+    {
         // placement, 4 elements (one 128-bit word of ba, one 8-byte word of partner slots) per step.  An element of a
         // boundary bucket stores its own index (the staged row doubles as the member list of such a bucket; it holds
         // >= n entries), any other element its partner slot.  Positions past the last threshold are overwritten with
         // kNoSlot after the ranking.  Only the two steps of the partial key block (n % 8 != 0) check e < n.
-        const uint32_t cnt_a = smem_addr(S.cnt), ba_a = smem_addr(S.ba), st_a = smem_addr(stage);
+        const uint32_t cnt_a = smem_addr(S.cnt), st_a = smem_addr(stage);
+        const uint32_t ba_a = BA_SHARED ? smem_addr(S.ba) : 0u;
         const uint32_t sh = 32u - (uint32_t)B;
         const bool tail = (n & 7u) != 0u;
         for (uint32_t u = tid; u < steps; u += nt) {
             const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
-            const uint4 va = lds128(ba_a + u * 16);
+            uint4 va;
+            if constexpr (BA_SHARED) va = lds128(ba_a + u * 16);
+            else va = ldg128_plain(S.ba + (size_t)u * 4);
             const uint2 dsv = __ldg(reinterpret_cast<const uint2 *>(P.dslot2 + e0));  // dslot2 is padded to a multiple of 8
             const uint32_t v[4] = {va.x, va.y, va.z, va.w};
             const uint32_t ds[4] = {dsv.x & 0xFFFFu, dsv.x >> 16, dsv.y & 0xFFFFu, dsv.y >> 16};
@@ -612,22 +632,6 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
                     const uint32_t pos = (w[q] & kPosMask) + (v[q] & 0xFFFFu);
                     if (e0 + q < n) sts16(st_a + 2 * pos, (int32_t)w[q] < 0 ? e0 + q : ds[q]);
                 }
-            }
-        }
-    } else {
-        const uint4 *ba4 = reinterpret_cast<const uint4 *>(S.ba);
-        for (uint32_t u = tid; u < steps; u += nt) {
-            const uint32_t e0 = u < n8 ? u * 8 : (u - n8) * 8 + 4;
-            const uint4 va = ba4[u];
-            const uint32_t v[4] = {va.x, va.y, va.z, va.w};
-            const uint2 dsv = *reinterpret_cast<const uint2 *>(P.dslot2 + e0);
-            const uint32_t ds[4] = {dsv.x & 0xFFFFu, dsv.x >> 16, dsv.y & 0xFFFFu, dsv.y >> 16};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t e = e0 + q;
-                const uint32_t w = S.cnt[v[q] >> (32 - B)];
-                const uint32_t pos = (w & kPosMask) + (v[q] & 0xFFFFu);
-                if (e < n) stage[pos] = (uint16_t)((w >> 31) ? e : ds[q]);
             }
         }
     }
@@ -666,8 +670,10 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
     __syncthreads();
 }
 
-template <bool BA_IN_SCRATCH>
-__global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed0,
+// NT threads per CTA: 1024 (one CTA per SM) or 512 (two CTAs per SM, each on its own permutation, so that the block
+// barriers and shared-memory round trips of one overlap with the other's work)
+template <bool BA_IN_SCRATCH, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) sigma_sort_kernel(const __grid_constant__ Problem P, uint64_t seed0,
                                                                    const uint64_t *__restrict__ seeds, uint32_t seg,
                                                                    uint64_t first_id, int n_tasks, int B1, int B2,
                                                                    uint16_t *__restrict__ pb,
@@ -719,7 +725,7 @@ __global__ void __launch_bounds__(kSigmaThreads) sigma_sort_kernel(const __grid_
         const uint64_t perm_id = first_id + (uint64_t)(seeds ? (uint32_t)t % seg : (uint32_t)t);
         uint16_t *dst = pb + (size_t)t * P.pb_stride;
         if (rowwise) {
-            block_place_rowwise<!BA_IN_SCRATCH>(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
+            block_place_rowwise<!BA_IN_SCRATCH, NT>(S, P, bounds, P.n2, B2, seed, perm_id, 0u, stage);
         } else if (identical) {
             // element = list-2 position e, rank f = the list-1 position it is paired with
             block_rank_by_random_keys(S, P.n2, B2, seed, perm_id, 0u, [&](uint32_t e, uint32_t f) {
@@ -1740,23 +1746,49 @@ int pick_bucket_bits(uint32_t n) {
     return B;
 }
 
+// ctas_per_sm: 0 = choose (two 512-thread CTAs per SM on the row-wise path when they fit, else one 1024-thread CTA),
+// 1 / 2 = force.  *grid_unit_out = CTAs one SM holds (the caller sizes the grid in multiples of sm_count x that).
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, const uint64_t *seeds, uint32_t seg, uint64_t first_id,
                               int n_tasks, uint16_t *pb, uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit,
-                              int grid, cudaStream_t st) {
+                              int sm_count, int ctas_per_sm, cudaStream_t st) {
     const int B1 = pick_bucket_bits(P.n1), B2 = pick_bucket_bits(P.n2);
-    const bool ba_in_smem = sigma_smem_bytes(P, B1, B2, true) <= smem_limit;
-    const size_t base = sigma_smem_bytes(P, B1, B2, ba_in_smem);
-    if (base > smem_limit || !scratch) return cudaErrorInvalidValue;
-    // whatever shared memory is left holds the boundary-bucket list (it spills to the global scratch beyond that)
+    if (!scratch) return cudaErrorInvalidValue;
+    const bool rowwise = (P.n_common == P.n1 && P.n_common == P.n2) && pairing_out == nullptr;
     const uint32_t nmax = P.n1 > P.n2 ? P.n1 : P.n2;
-    const size_t list_cap = std::min<size_t>((smem_limit - base) / 4 & ~(size_t)3, (nmax + 7) & ~7u);
+    // two CTAs per SM: each may use half of the SM's shared memory minus the 1 KB the system reserves per CTA
+    const size_t half_limit = ((size_t)228 * 1024) / 2 - 1024;
+    // Measured on a B200 (profiles/r02_sigma_ctas_ab.json): two CTAs per SM win 24 % at N = 6 000, where the (key16 |
+    // arrival) words of both fit in shared memory; at N = 20 000 they only fit with those words in the L2 scratch, and that
+    // costs more (+7 %) than the overlap of the two CTAs' barriers gains -- so: two CTAs only with everything on chip.
+    int per_sm = 1;
+    const bool fits_two_lean = sigma_smem_bytes(P, B1, B2, false) + 1024 <= half_limit && (1u << B2) <= 32u * 512u;
+    const bool fits_two_onchip = sigma_smem_bytes(P, B1, B2, true) + 1024 <= half_limit && (1u << B2) <= 32u * 512u;
+    if (rowwise && ((ctas_per_sm == 0 && fits_two_onchip) || (ctas_per_sm == 2 && fits_two_lean))) per_sm = 2;
+    if (ctas_per_sm == 2 && per_sm != 2) return cudaErrorInvalidValue;
+    const size_t limit = per_sm == 2 ? half_limit : smem_limit;
+    const bool ba_in_smem = sigma_smem_bytes(P, B1, B2, true) <= limit;
+    const size_t base = sigma_smem_bytes(P, B1, B2, ba_in_smem);
+    if (base > limit) return cudaErrorInvalidValue;
+    // whatever shared memory is left holds the boundary-bucket list (it spills to the global scratch beyond that)
+    const size_t list_cap = std::min<size_t>((limit - base) / 4 & ~(size_t)3, (nmax + 7) & ~7u);
     const size_t smem = base + list_cap * 4;
-    auto kern = ba_in_smem ? sigma_sort_kernel<false> : sigma_sort_kernel<true>;
-    static std::atomic<uint64_t> done_a{0}, done_b{0};
-    cudaError_t e = set_max_smem_once(reinterpret_cast<const void *>(kern), ba_in_smem ? done_a : done_b);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, kSigmaThreads, smem, st>>>(P, seed, seeds, seg ? seg : 1u, first_id, n_tasks, B1, B2, pb, pairing_out, scratch,
-                                            (uint32_t)list_cap);
+    const int grid = std::min(n_tasks, sm_count * 4);  // a multiple of sm_count x per_sm; the scratch holds sm_count x 4 CTAs
+    static std::atomic<uint64_t> done[4];
+    cudaError_t e;
+#define DTO_SIGMA(SCR, NTH, SLOT)                                                                                         \
+    {                                                                                                                      \
+        auto kern = sigma_sort_kernel<SCR, NTH>;                                                                           \
+        e = set_max_smem_once(reinterpret_cast<const void *>(kern), done[SLOT]);                                           \
+        if (e != cudaSuccess) return e;                                                                                    \
+        kern<<<grid, NTH, smem, st>>>(P, seed, seeds, seg ? seg : 1u, first_id, n_tasks, B1, B2, pb, pairing_out, scratch, \
+                                      (uint32_t)list_cap);                                                                 \
+    }
+    if (per_sm == 2) {
+        if (ba_in_smem) DTO_SIGMA(false, 512, 0) else DTO_SIGMA(true, 512, 1)
+    } else {
+        if (ba_in_smem) DTO_SIGMA(false, 1024, 2) else DTO_SIGMA(true, 1024, 3)
+    }
+#undef DTO_SIGMA
     return cudaGetLastError();
 }
 

@@ -32,7 +32,7 @@ cudaError_t launch_scan_counts(uint32_t *counts, int n, unsigned long long *tota
 cudaError_t launch_fill_lptab(const Problem &P, const uint32_t *offsets, uint2 *meta, double *lptab, cudaStream_t st);
 cudaError_t launch_sigma_sort(const Problem &P, uint64_t seed, const uint64_t *seeds, uint32_t seg, uint64_t first_id,
                               int n_tasks, uint16_t *pb, uint32_t *pairing_out, uint32_t *scratch, size_t smem_limit,
-                              int grid, cudaStream_t st);
+                              int sm_count, int ctas_per_sm, cudaStream_t st);
 cudaError_t launch_compose(const Problem &P, const uint32_t *perm1, const uint32_t *perm2, const int32_t *slot2_maps,
                            int n_tasks, uint32_t *inv_scratch, int *err_flag, uint16_t *pb, cudaStream_t st);
 cudaError_t launch_scan(const Problem &P, const uint16_t *pb, int n_tasks, int n_plain, uint32_t flags, dto_b200_record *out,
