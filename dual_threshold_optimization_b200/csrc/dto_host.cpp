@@ -572,10 +572,14 @@ int dto_b200_run_pairs(const dto_b200_ranked_list *const *lists1, const dto_b200
                     grp->err = dto_b200_last_error();
                 }
                 if (ident) {
+                    // keep a group's partner-slot rows (2 B per list-1 position and task) under 6 GiB
+                    const size_t row_bytes = 2 * (lists1[q]->ids.size() + 256);
+                    const size_t by_memory = std::max<size_t>(1, (((size_t)6 << 30) / row_bytes) / (permutations + 1));
+                    const size_t group_cap = std::min(max_group, by_memory);
                     grp->batched = true;
                     grp->slot_maps = slot;
                     grp->seeds.push_back(pair_seed(seed, q));
-                    while (e < hi && e - q < max_group && populations[e] == populations[q] && same_ranks(lists1[e], lists1[q]) &&
+                    while (e < hi && e - q < group_cap && populations[e] == populations[q] && same_ranks(lists1[e], lists1[q]) &&
                            same_ranks(lists2[e], lists2[q])) {
                         std::vector<int32_t> s2;
                         if (slot_map_of(lists1[e], lists2[e], s2) != DTO_B200_OK) break;  // reported when it leads its own group

@@ -1341,35 +1341,33 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
                 if (lane >= o) inc2 += v;
             }
             const uint32_t koff2 = inc2 - run2;  // overlap contributed by the lanes to the left, in both halves
-            // (3) screen: only k >= kcrit can have p <= tau_level
-            auto screen = [&](int q) {
-                const uint32_t kk = kcur2[q] + koff2;  // no carry between the halves: every k < 65536
-                const uint32_t k0 = kk & 0xFFFFu, k1 = kk >> 16;
-                if (k0 >= (kc2[q] & 0xFFFFu)) {
-                    const uint32_t slot = atomicAdd(qcnt, 1u);
-                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q);
-                    Qk[slot] = (uint16_t)k0;
-                }
-                if (k1 >= (kc2[q] >> 16)) {
-                    const uint32_t slot = atomicAdd(qcnt, 1u);
-                    Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q + 1);
-                    Qk[slot] = (uint16_t)k1;
+            // (3) screen: only k >= kcrit can have p <= tau_level.  Packed compare of both 16-bit fields at once, branch-free;
+            // `ge2(q)` has bit 15 / bit 31 set iff the low / high column of pair q passes.
+            //  * SWAR (every set size <= 32 766): field = k + 0x8000 - kcrit keeps its top bit iff k >= kcrit (all values
+            //    < 0x8000, "never" = 0x7FFF, so no borrow crosses the fields): 2 instructions per pair;
+            //  * longer lists (full 16-bit fields, "never" = 0xFFFF): compare the low 15 bits the same way, then settle the
+            //    top bits: a >= b  <=>  (a15 & ~b15) | (~(a15 ^ b15) & low15(a) >= low15(b)): 5 instructions per pair.
+            // One warp vote per row; 8 % of the rows have a passing cell, and only then each pair is revisited.
+            const uint32_t bias = koff2 + 0x80008000u;
+            auto ge2 = [&](int q) -> uint32_t {
+                if constexpr (SWAR) {
+                    return kcur2[q] + bias - kc2[q];
+                } else {
+                    const uint32_t a = kcur2[q] + koff2, bq = kc2[q];
+                    const uint32_t d = (a | 0x80008000u) - (bq & 0x7FFF7FFFu);
+                    return (a & ~bq) | (~(a ^ bq) & d);
                 }
             };
-            if constexpr (SWAR) {
-                // packed 15-bit compare, branch-free: field = k + 0x8000 - kcrit keeps its top bit iff k >= kcrit (all
-                // values < 0x8000, "never" = 0x7FFF, so no borrow crosses the fields); one test per row
-                const uint32_t bias = koff2 + 0x80008000u;
-                uint32_t hit = 0;
+            uint32_t hit = 0;
 #pragma unroll
-                for (int q = 0; q < NP; ++q) hit |= (kcur2[q] + bias - kc2[q]);
-                if (__any_sync(kFull, (hit & 0x80008000u) != 0u)) {  // some lane has a passing cell (8 % of the rows)
-                  if (hit & 0x80008000u) {  // revisit the pairs, each guarded by its own test
+            for (int q = 0; q < NP; ++q) hit |= ge2(q);
+            if (__any_sync(kFull, (hit & 0x80008000u) != 0u)) {  // some lane has a passing cell
+                if (hit & 0x80008000u) {  // revisit the pairs, each guarded by its own test
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
-                        const uint32_t h = (kcur2[q] + bias - kc2[q]) & 0x80008000u;
+                        const uint32_t h = ge2(q) & 0x80008000u;
                         if (h) {
-                            const uint32_t kk = kcur2[q] + koff2;
+                            const uint32_t kk = kcur2[q] + koff2;  // no carry between the halves: every k < 65536
                             if (h & 0x8000u) {
                                 const uint32_t slot = atomicAdd(qcnt, 1u);
                                 Qij[slot] = ((uint32_t)i << 16) | (uint32_t)(lane * CH + 2 * q);
@@ -1382,13 +1380,7 @@ __device__ __noinline__ void scan_rows(const Problem &P, RowState<CH> &st, const
                             }
                         }
                     }
-                  }
-                  __syncwarp();
-                  qn = *qcnt;
                 }
-            } else {
-#pragma unroll
-                for (int q = 0; q < NP; ++q) screen(q);
                 __syncwarp();
                 qn = *qcnt;
             }
