@@ -597,6 +597,9 @@ __device__ void block_place_rowwise(const SortShared &S, const Problem &P, const
         base = __shfl_sync(kFull, base, 31) + inc - m;
         for (uint32_t y = 0; y < m; ++y) lst_put(base + y, (own[r] << 16) | y);
     }
+    // the previous permutation's staged row is still being read by its bulk copy-out (issued by thread 0 after the last
+    // barrier of that permutation): the placement below is the first phase to overwrite it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
     const uint32_t n8 = (n + 7) >> 3;
     const uint32_t steps = 2 * n8;
@@ -749,14 +752,27 @@ __global__ void __launch_bounds__(NT, 1024 / NT) sigma_sort_kernel(const __grid_
             for (uint32_t x = P.n1_eff + tid; x < P.pb_stride; x += nt) stage[x] = kNoSlot;
             __syncthreads();
         }
-        // coalesced copy-out, 16 bytes per thread (pb_stride is a multiple of 256, rows are 512 B aligned); the row-wise
-        // variant clears its bucket counters for the next permutation in the same phase
-        const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-        for (uint32_t x = tid; x < P.pb_stride / 8; x += nt) d4[x] = s4[x];
-        if (rowwise) block_zero_counters_fast(S, B2);
+        // copy-out (pb_stride is a multiple of 256, rows are 512 B aligned); the row-wise variant clears its bucket
+        // counters for the next permutation in the same phase
+        if (rowwise) {
+            // one 1-D bulk copy (TMA) of the whole row, shared -> global, issued by one thread and overlapped with the
+            // next permutation's key pass, block scan and boundary search, none of which touch the staged row
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the row was written through the generic proxy
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(stage)),
+                             "r"(P.pb_stride * 2u)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            block_zero_counters_fast(S, B2);
+        } else {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+            for (uint32_t x = tid; x < P.pb_stride / 8; x += nt) d4[x] = s4[x];
+        }
         __syncthreads();
     }
+    if (rowwise && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the CTA's shared memory outlives the copy
 }
 
 // =====================================================================================================
