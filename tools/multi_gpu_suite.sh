@@ -4,6 +4,7 @@
 # gpurun_out/<tag>_n<N>_<config>_<scaling>.json
 N=${1:-2}
 TAG=${2:-r02}
+WHAT=${3:-"tests c3:weak c3:strong c4:strong c5:weak c5:strong"}
 PORT=29517
 run() {  # config scaling extra-args...
   local c=$1 s=$2; shift 2
@@ -20,9 +21,6 @@ except Exception as e:
 PY
 }
 nvidia-smi -L | head -8
-python -m pytest tests -m gpu -x -q -k "multi_gpu or allgather" 2>&1 | tail -5
-run c3 weak
-run c3 strong
-run c4 strong
-run c5 weak
-run c5 strong
+for w in $WHAT; do
+  if [ $w = tests ]; then python -m pytest tests -m gpu -x -q -k "multi_gpu or allgather" 2>&1 | tail -5; else run ${w%%:*} ${w##*:}; fi
+done
