@@ -191,6 +191,16 @@ def workload_string(args, cfg_name):
     return CONFIGS[cfg_name]["label"]
 
 
+def nominal_permutations_per_step(args):
+    """permutations one step of the workload stands for, over all GPUs (what `config.permutations_per_step` says)"""
+    c = CONFIGS[args.config]
+    if args.config == "c4":
+        return (args.pairs or c["pairs"]) * (args.perms or c["perms_per_pair"])
+    if args.scaling == "strong":
+        return args.perms or c.get("perms_strong", c["perms"])
+    return (args.perms or c["perms"]) * max(args.gpus, 1)
+
+
 def run_reference_arm(args, rank):
     """The reference's own CPU algorithm for this path on the box's host cores: the oracle port in reference-faithful mode
     (the Rust crate cannot be built in this image), every host thread, a bounded sample per step."""
@@ -204,7 +214,10 @@ def run_reference_arm(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * w["seconds"] / max(args.steps, 1),
         "higher_is_better": True, "scaling": args.scaling if args.config != "c4" else "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_string(args, args.config), "features": w["features"], "threshold_pairs": w["threshold_pairs"]},
+        # the workload of the product arm (same keys, same values); what one step of THIS arm actually times -- a bounded
+        # sample of it -- is described in cpu_baseline.sample
+        "config": {"workload": workload_string(args, args.config), "features": w["features"], "threshold_pairs": w["threshold_pairs"],
+                   "permutations_per_step": nominal_permutations_per_step(args)},
         "cpu_baseline": {"value": value, "unit": unit, "cores": w["cores"], "kind": "port",
                          "sample": (f"reference-faithful oracle mode (string ids, per-cell hash set, uncached ln_gamma, full tails); each step = "
                                     f"{w['perms_per_step']} permutations on {w['cores']} threads, every {w['stride']}th t1 row of the grid, "
@@ -622,7 +635,7 @@ def bench_pairs(args, cfg, dto, eng, clocks, rank, world, local_rank, barrier, m
             "ms_per_step": 1e3 * wall_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": workload_string(args, args.config), "features": n, "threshold_pairs": T * T, "pairs": n_pairs,
-                       "permutations_per_pair": P, "pairs_per_s": pairs_per_s, "pvalue_evals_per_s": (value + pairs_per_s) * T * T,
+                       "permutations_per_pair": P, "permutations_per_step": n_pairs * P, "pairs_per_s": pairs_per_s, "pvalue_evals_per_s": (value + pairs_per_s) * T * T,
                        "l2_policy": "every pair brings new lists and every step new permutation ids; ~1.5 GB of partner-slot rows per launch (126 MB L2)",
                        "list_build_s_rank0": build_s},
             "e2e": {"value": value, "unit": "permutations/s", "h2d_bytes_per_step": int((tot1["h2d_bytes"] - tot0["h2d_bytes"]) // args.steps),

@@ -39,3 +39,47 @@ def test_product_arm_fails_loudly_without_gpu():
     assert r.returncode != 0
     assert "CUDA" in r.stderr or "NVIDIA" in r.stderr
     assert not r.stdout.strip()  # no JSON line is fabricated
+
+
+def test_ncu_capture_is_refused_for_other_kernel_sources(tmp_path, monkeypatch):
+    """bench.py's roofline reads per-kernel instruction counts from an ncu capture; a capture taken from other kernel
+    sources must be refused, not silently multiplied into this run's rate."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    sha = bench.kernel_source_sha()
+    assert len(sha) == 16 and sha == bench.kernel_source_sha()
+    d, why = bench.load_ncu_captures("c3")
+    if d is not None:
+        assert d["kernel_source_sha"] == sha and {"scan", "sigma"} <= set(d)
+    else:
+        assert "refused" in why or "no capture" in why
+    monkeypatch.setattr(bench, "kernel_source_sha", lambda: "0" * 16)
+    d, why = bench.load_ncu_captures("c3")
+    assert d is None and ("refused" in why or "no capture" in why)
+
+
+def test_nominal_workload_sizes_and_sharding():
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+
+    def ns(**kw):
+        base = dict(config="c3", scaling="weak", perms=0, pairs=0, gpus=1)
+        base.update(kw)
+        return argparse.Namespace(**base)
+
+    assert bench.nominal_permutations_per_step(ns()) == 100000
+    assert bench.nominal_permutations_per_step(ns(gpus=8)) == 800000
+    assert bench.nominal_permutations_per_step(ns(gpus=8, scaling="strong")) == 100000
+    assert bench.nominal_permutations_per_step(ns(config="c5", gpus=8)) == 1000000
+    assert bench.nominal_permutations_per_step(ns(config="c5", gpus=8, scaling="strong")) == 1000000
+    assert bench.nominal_permutations_per_step(ns(config="c4", gpus=8)) == 2000000
+    for total in (0, 1, 7, 100000, 100001):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = bench.shard(total, world, r)
+                got.extend(range(lo, hi))
+            assert got == list(range(total))
