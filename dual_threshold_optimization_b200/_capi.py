@@ -172,6 +172,7 @@ SYMBOLS = {
         C.c_int,
         [C.POINTER(_vp), C.POINTER(_vp), _u64p, C.c_size_t, C.c_size_t, C.POINTER(C.c_int), C.c_size_t, C.c_uint64, C.POINTER(FinalResult)],
     ),
+    "dto_b200_hypergeometric_pvalue_host": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _f64p]),
     "dto_b200_fdr": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, _f64p]),
     "dto_b200_empirical_pvalue": (C.c_int, [_recp, C.c_size_t, C.POINTER(FinalResult)]),
     "dto_b200_final_result_json": (C.c_int, [C.POINTER(FinalResult), C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -668,6 +668,18 @@ int dto_b200_fdr(uint64_t list1_len, uint64_t list2_len, uint64_t overlap, uint6
     return DTO_B200_OK;
 }
 
+// hypergeometric_pvalue (src/stat_operations/hypergeometric_pvalue.rs:33-50) on the HOST, exactly as the tie resolver and
+// the epilogue evaluate it: statrs operation order over the host-built ln-factorial table, host libm exp()
+int dto_b200_hypergeometric_pvalue_host(uint64_t N, uint64_t K, uint64_t n, uint64_t k, double *pvalue_out) {
+    if (!pvalue_out) return fail(DTO_B200_ERR_INVALID, "null pvalue_out");
+    if (K > N || n > N)
+        return fail(DTO_B200_ERR_PANIC, "Failed to create hypergeometric distribution: successes %llu / draws %llu > population %llu",
+                    (unsigned long long)K, (unsigned long long)n, (unsigned long long)N);
+    if (N > ((uint64_t)1 << 27)) return fail(DTO_B200_ERR_UNSUPPORTED, "population exceeds 2^27");
+    *pvalue_out = dto::host_hypergeom_pvalue_exact(host_lf_table(N)->data(), N, K, n, k);
+    return DTO_B200_OK;
+}
+
 int dto_b200_empirical_pvalue(const dto_b200_record *records, size_t n, dto_b200_final_result *out) {
     if (!out || (n && !records)) return fail(DTO_B200_ERR_INVALID, "null argument");
     const dto_b200_record *unperm = nullptr;

@@ -259,6 +259,11 @@ int dto_b200_run_tasks(const dto_b200_ranked_list *l1, const dto_b200_ranked_lis
                        const uint64_t *task_ids, const uint8_t *task_permute, size_t n_tasks, const int *devices,
                        size_t n_devices, uint64_t seed, dto_b200_record *records_out);
 
+/* hypergeometric_pvalue (src/stat_operations/hypergeometric_pvalue.rs:33-50) evaluated on the HOST the way the library's
+ * tie resolver and epilogue do: statrs operation order, host-built ln-factorial table, host libm exp().  Bit-identical to
+ * the reference on this machine (pinned to the reference's goldens by tests/test_host_layer.py); needs no GPU. */
+int dto_b200_hypergeometric_pvalue_host(uint64_t N, uint64_t K, uint64_t n, uint64_t k, double *pvalue_out);
+
 /* fdr (src/stat_operations/fdr.rs:29-60); sensitivity <= 0 -> DTO_B200_ERR_PANIC */
 int dto_b200_fdr(uint64_t list1_len, uint64_t list2_len, uint64_t overlap, uint64_t population, double sensitivity,
                  double *fdr_out);

@@ -238,3 +238,27 @@ def test_limits_query_and_feature_list_reader(tmp_path):
     p.write_text(" a \r\nb\n\n c\n")
     bg = dto.read_feature_list_from_file(str(p))
     assert bg.ids() == ["a", "b", "", "c"]  # every line counts, blank ones too (read_feature_list_from_file.rs:48-52)
+
+
+def test_host_evaluator_is_pinned_to_the_reference_goldens_and_the_oracle():
+    """The product's own host evaluation of hypergeometric_pvalue (what settles tie sets and the epilogue's `<=`): bit-exact
+    on the reference-held goldens (hypergeometric_pvalue.rs:27-31, :56-87) and on random quadruples against the oracle."""
+    L = capi.lib()
+
+    def host_p(N, K, n, k):
+        out = C.c_double()
+        capi.check(L.dto_b200_hypergeometric_pvalue_host(N, K, n, k, C.byref(out)))
+        return out.value
+
+    assert host_p(1000, 50, 60, 10) == 0.00044068070222441115
+    assert host_p(6060, 5808, 154, 153) == 0.010413637619010246
+    assert host_p(10, 1, 1, 0) == 1.0 and host_p(3, 1, 3, 1) == 1.0
+    rng = np.random.default_rng(5)
+    for N in (30, 3000, 20000):
+        lf = O.ln_factorial_table(N)
+        for _ in range(300):
+            K, n = int(rng.integers(0, N + 1)), int(rng.integers(0, N + 1))
+            k = int(rng.integers(0, min(K, n) + 1))
+            assert host_p(N, K, n, k) == O.hypergeometric_pvalue_cached(lf, N, K, n, k), (N, K, n, k)
+    with pytest.raises(dto.DtoPanic):
+        host_p(10, 11, 3, 1)
