@@ -580,6 +580,24 @@ def bench_single(args, cfg, dto, capi, eng, clocks, rank, world, local_rank, bar
     return line
 
 
+def pairs_roofline(tasks_per_s, sm_mhz):
+    """c4 runs the N = 6000 instantiations of the two kernels (the c2 capture) inside a batched driver: whole-job issue
+    utilisation = warp instructions per task x tasks/s (wall clock, host work included) / issue peak."""
+    ncu, why = load_ncu_captures("c2")
+    peak = 148 * 4 * sm_mhz * 1e6
+    if not ncu:
+        return {"bound": "issue", "achieved": None, "peak": peak / 1e9, "unit": "Gwarp-inst/s", "frac": None, "traffic": None,
+                "note": f"no valid ncu capture of the N = 6000 kernels for this build ({why})"}
+    wi = ncu["scan"]["warp_instructions_per_permutation"] + ncu["sigma"]["warp_instructions_per_permutation"]
+    rate = wi * tasks_per_s
+    return {"bound": "issue", "achieved": rate / 1e9, "peak": peak / 1e9, "unit": "Gwarp-inst/s", "frac": rate / peak,
+            "traffic": (ncu["scan"]["dram_bytes_per_permutation"] + ncu["sigma"]["dram_bytes_per_permutation"]) * tasks_per_s,
+            "warp_instructions_per_permutation": wi, "kernel_source_sha": ncu["kernel_source_sha"],
+            "note": ("whole job through dto_b200_run_pairs on the wall clock (host canonicalisation, uploads, epilogue included): warp instructions per task "
+                     "of the N = 6000 kernels (ncu capture of this build, profiles/kernel_counters_c2.json) x tasks/s vs 148 SMs x 4 schedulers x SM clock; "
+                     "`traffic` is DRAM bytes per second here, not per launch (launch sizes vary with the grouping)")}
+
+
 def bench_pairs(args, cfg, dto, eng, clocks, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks, run_pairs_structs):
     """c4: the batch of list pairs, sharded by pair over ranks; every step = the whole batch through dto_b200_run_pairs
     (per pair: slot map from string ids, lists up, unpermuted task + 1 000 Philox permutations, records down, epilogue)."""
@@ -642,8 +660,7 @@ def bench_pairs(args, cfg, dto, eng, clocks, rank, world, local_rank, barrier, m
                     "d2h_bytes_per_step": int((tot1["d2h_bytes"] - tot0["d2h_bytes"]) // args.steps), "steps": args.steps,
                     "path": "dto_b200_run_pairs on list handles (one context per GPU): value and e2e are the same call here -- every pair's lists are new host data by definition"},
             "gpu_launches": int(tot1["launches"] - tot0["launches"]), "clocks": clk,
-            "roofline": {"bound": "issue", "note": "same kernels as c2 (N = 6000): see `python bench.py --config c2`; this line measures the batched driver around them",
-                         "achieved": None, "peak": None, "unit": "Gwarp-inst/s", "frac": None, "traffic": None},
+            "roofline": pairs_roofline(value + pairs_per_s, (clk or {}).get("sm_mhz") or 1965.0),
             "cpu_baseline": cpu,
             "pairs_significant_at_0.01": sig,
         }
