@@ -252,7 +252,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--perms", type=int, default=0, help="override the permutations per step of the workload")
     ap.add_argument("--pairs", type=int, default=0, help="c4: override the number of list pairs")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-row-stride", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0)
