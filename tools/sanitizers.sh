@@ -3,4 +3,4 @@ for tool in memcheck racecheck; do
   ( echo "# compute-sanitizer --tool $tool python -c 'import __graft_entry__ as g; g.smoke()'"; timeout 600 compute-sanitizer --tool $tool python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | grep -v "^$" | tail -6 ) > gpurun_out/san_${tool}.txt
   ( echo "# compute-sanitizer --tool $tool python -m pytest tests -m gpu -x -q -k \"$K\""; timeout 900 compute-sanitizer --tool $tool python -m pytest tests -m gpu -x -q -k "$K" 2>&1 | grep -v "^$" | tail -8 ) > gpurun_out/san_${tool}_tests.txt
 done
-tail -3 gpurun_out/san_*.txt
+for f in gpurun_out/san_*.txt; do tail -n 3 $f; done
