@@ -31,7 +31,7 @@ extern "C" {
 #define DTO_B200_ERR_CUDA (-2)        /* CUDA runtime failure / no device */
 #define DTO_B200_ERR_STATE (-3)       /* call order: no problem set */
 #define DTO_B200_ERR_PANIC (-4)       /* a condition on which the reference panics (message mirrors the reference) */
-#define DTO_B200_ERR_UNSUPPORTED (-5) /* outside the implemented envelope (see dto_b200_limits) */
+#define DTO_B200_ERR_UNSUPPORTED (-5) /* outside the implemented envelope (dto_b200_get_limits) */
 #define DTO_B200_ERR_IO (-6)
 
 /* Mirrors OptimizationResultRecord, src/dto/results_objects.rs:22-32 (feature_sets = FeatureSets::None). */
