@@ -262,3 +262,26 @@ def test_host_evaluator_is_pinned_to_the_reference_goldens_and_the_oracle():
             assert host_p(N, K, n, k) == O.hypergeometric_pvalue_cached(lf, N, K, n, k), (N, K, n, k)
     with pytest.raises(dto.DtoPanic):
         host_p(10, 11, 3, 1)
+
+
+def test_cli_without_gpu_fails_loudly_and_prints_version():
+    """The CLI drop-in (src/main.rs flags): --version / --help work anywhere; a run without a usable GPU exits non-zero with
+    the library's message instead of computing anything on the CPU."""
+    import subprocess
+
+    import torch
+
+    cli = capi.CLI_PATH
+    v = subprocess.run([cli, "--version"], capture_output=True, text=True, timeout=60)
+    assert v.returncode == 0 and "dual_threshold_optimization 2.0.1" in v.stdout and "sm_100a" in v.stdout
+    h = subprocess.run([cli, "--help"], capture_output=True, text=True, timeout=60)
+    assert h.returncode == 0 and "--ranked-list1" in h.stdout and "--permutations" in h.stdout and "--multi-node" in h.stdout
+    miss = subprocess.run([cli, "-1", "a.csv"], capture_output=True, text=True, timeout=60)
+    assert miss.returncode == 2 and "--ranked-list2" in miss.stderr
+    if torch.cuda.is_available():
+        return
+    td = os.path.join(H.GOLDEN, "test_data")
+    r = subprocess.run([cli, "-1", f"{td}/ranklist1.csv", "-2", f"{td}/ranklist2.csv", "-p", "10"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and not r.stdout.strip()
+    assert "no CUDA device" in r.stderr or "CUDA" in r.stderr
+    assert "Ranked list 1:" in r.stderr and "Permutations: 10" in r.stderr  # the run-information lines come first, as in main.rs:78-88
