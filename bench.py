@@ -481,6 +481,40 @@ def bench_single(args, cfg, dto, capi, eng, clocks, rank, world, local_rank, bar
     d2h_step = (tot1["d2h_bytes"] - tot0["d2h_bytes"] + e2e_copy_bytes[1]) // max(args.e2e_steps, 1)
     e2e_launches = tot1["launches"] - tot0["launches"]
 
+    # ---- the same job through ONE process driving all GPUs: dto_b200_run_tasks(devices = [0 .. N-1]) -- what `-m` of the CLI
+    # maps to, the single-box replacement of src/run/multi_node.rs:114-161.  Rank 0 alone runs it (the other ranks wait at
+    # the barrier with idle GPUs); reported next to the process-per-GPU figure, not instead of it. ----
+    in_process = None
+    if world > 1:
+        store = dist.distributed_c10d._get_default_store()
+        torch.cuda.synchronize()
+        if rank == 0:
+            ids_all = np.zeros(1 + per_step_all, dtype=np.uint64)
+            perm_all = np.ones(1 + per_step_all, dtype=np.uint8)
+            perm_all[0] = 0
+            out_all = np.zeros(1 + per_step_all, dtype=capi.RECORD_DTYPE)
+            devs = list(range(world))
+
+            def in_process_step(step_idx):
+                first = 1 + (70_000 + step_idx) * per_step_all
+                ids_all[1:] = np.arange(first, first + per_step_all, dtype=np.uint64)
+                recs = run_single_node_records((ids_all, perm_all), l1, l2, population, 1, devs, PHILOX_SEED, out=out_all)
+                return empirical_pvalue_struct(recs).empirical_pvalue
+
+            in_process_step(-1)
+            t0 = time.perf_counter()
+            for s in range(args.e2e_steps):
+                in_process_step(s)
+            dt = time.perf_counter() - t0
+            in_process = {"value": per_step_all * args.e2e_steps / dt, "unit": "permutations/s", "steps": args.e2e_steps, "devices": devs,
+                          "path": "one process, dto_b200_run_tasks(devices = all GPUs) + dto_b200_empirical_pvalue; host threads, no NCCL"}
+            store.set("dto_in_process_done", "1")
+        else:
+            # wait on the CPU (the rendezvous store), not in an NCCL barrier: a spinning NCCL kernel of this process would
+            # time-slice this GPU against rank 0's kernels
+            store.wait(["dto_in_process_done"])
+        barrier()
+
     line = None
     if rank == 0:
         peaks = {}
@@ -566,7 +600,7 @@ def bench_single(args, cfg, dto, capi, eng, clocks, rank, world, local_rank, bar
                        "pvalue_evals_per_s": value * T1 * T2},
             "device_only_value": value_device_only,
             "e2e": {"value": e2e_value, "unit": "permutations/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
-                    "steps": args.e2e_steps, "empirical_pvalue": e2e_emp, "gpu_launches": int(e2e_launches),
+                    "steps": args.e2e_steps, "empirical_pvalue": e2e_emp, "gpu_launches": int(e2e_launches), "in_process_all_gpus": in_process,
                     "path": "dto_b200_run_tasks (list handles -> records on the host) + dto_b200_empirical_pvalue" + (", records gathered over NCCL" if world > 1 else "")},
             "gpu_launches": int(launches),
             "clocks": clk,
